@@ -1,0 +1,726 @@
+// mcs_api.cu — C-ABI (include/mcs.h) of the B200 transport loop: device memory, launches, NCCL.
+//
+// Every entry point replaces a piece of /root/reference/src/main_loops.jl (see include/mcs.h).  The library
+// owns all device state; callers pass plain host pointers.  NCCL is resolved with dlopen at mcs_comm_init so
+// that single-GPU users need no NCCL at all and multi-GPU users share the libnccl their process already has.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "mcs_device.cuh"
+
+using namespace mcs;
+
+static thread_local char g_err[768];
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(MCS_ERR_CUDA, "CUDA error: %s at %s", cudaGetErrorString(e_), #call); \
+    } while (0)
+
+extern "C" const char* mcs_last_error(void) { return g_err; }
+extern "C" const char* mcs_backend(void) { return "cuda-sm_100a"; }
+
+extern "C" int mcs_abi_sizes(int32_t out[6]) {
+    out[0] = (int32_t)sizeof(McsConfig); out[1] = (int32_t)sizeof(McsSpecies); out[2] = (int32_t)sizeof(McsTallies);
+    out[3] = (int32_t)sizeof(McsPopulation); out[4] = (int32_t)sizeof(McsTraceRec); out[5] = (int32_t)sizeof(McsTiming);
+    return MCS_OK;
+}
+
+extern "C" void mcs_default_config(McsConfig* c) {
+    memset(c, 0, sizeof *c);
+    c->abi_version = MCS_ABI_VERSION; c->device = -1;
+    c->mp_g = 1.67262192369e-24; c->c_cms = 2.99792458e10; c->qcgs_esu = 4.80320471257e-10;
+    c->E_rel_pt = 0.005;
+    {
+        double me = 9.1093837015e-28, sigT = 6.6524587321e-25, cc = c->c_cms;
+        c->rad_loss_fac = 4.0 / 3.0 * cc * sigT / (cc * cc * cc * me * me * 8 * PI);  // constants.jl:30
+    }
+    c->eta_mfp = 1.0; c->xn_per_fine = 2000.0; c->xn_per_coarse = 100.0; c->age_max = -1.0;
+    c->pe_crit = -1.0; c->gam_e_crit = -1.0;
+    c->n_ions = 1; c->na_cr = 1000000; c->n_pts_max = 100000;
+    for (int i = 0; i < MCS_MAX_IONS; i++) c->inj_fracs[i] = 1.0;
+    c->do_retro = 1;
+    c->helix_cap = 10000; c->retro_cap = 10000000; c->seed = 210; c->compat = MCS_COMPAT_DEFAULT;
+    c->rng_mode = MCS_RNG_PHILOX; c->threads = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return MCS_OK;
+    const char* names[] = {getenv("MCS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        if (!n) continue;
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(MCS_ERR_COMM, "cannot dlopen libnccl.so.2 (set MCS_NCCL_LIB): %s", dlerror());
+#define SYM(field, name)                                                       \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(lib, name);                   \
+    if (!g_nccl.field) return fail(MCS_ERR_COMM, "libnccl lacks %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(AllReduce, "ncclAllReduce")
+    SYM(AllGather, "ncclAllGather") SYM(CommDestroy, "ncclCommDestroy") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = lib;
+    return MCS_OK;
+}
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        ncclResult_t r_ = (call);                                                                       \
+        if (r_ != ncclSuccess) return fail(MCS_ERR_COMM, "NCCL error: %s at %s", g_nccl.GetErrorString(r_), #call); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+struct McsHandle {
+    McsConfig cfg;
+    McsSpecies sp;
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    bool have_profile = false, have_ion = false;
+    int i_iter = 0, i_ion = 0;
+    int ng = 0, M = 0, T = 0;
+    long long n_use = 0, first_global = 0, n_saved_last = 0, n_saved_global_last = 0;
+    // device buffers
+    double* d_grid = nullptr;  // 10 arrays of (ng+2): xg ux uz ut gsf gef bt sinth costh (bef unused) + tcuts(NA_C)
+    double* d_zone = nullptr;  // eps_target, recv_pool [ng] each
+    PopPtrs pop[3];            // cur, saved, next
+    int cur = 0, nxt = 2;      // saved is always pop[1]
+    uint8_t* d_l_save = nullptr;
+    int *d_fate = nullptr, *d_helix = nullptr;
+    long long *d_retro = nullptr, *d_draws = nullptr, *d_saved_idx = nullptr, *d_block_off = nullptr, *d_total = nullptr;
+    int* d_block_cnt = nullptr;
+    // tallies: one packed FP64 buffer (single all-reduce) + one packed u64 buffer
+    double* d_tally = nullptr;
+    size_t n_tally = 0, off_pxx = 0, off_pxz = 0, off_efl = 0, off_psd = 0, off_esc_up = 0, off_esc_dn = 0, off_en_eff = 0,
+           off_num_eff = 0, off_wc = 0, off_sc = 0, off_pool = 0, off_sf = 0, off_pf = 0, off_scal = 0;
+    unsigned long long* d_u64 = nullptr;  // [ng crossings | CNT_N counters]
+    unsigned long long h_counters[CNT_N];
+    long long *d_tg = nullptr;
+    double *d_tpx = nullptr, *d_tpt = nullptr, *d_tw = nullptr;
+    double* d_partials = nullptr;
+    int max_blocks = 0, block = 256, blocks_per_sm = 2;
+    // debug
+    double* d_replay_u = nullptr;
+    long long* d_replay_off = nullptr;
+    long long replay_n = 0;
+    int* d_trace_slot = nullptr;
+    McsTraceRec* d_trace_recs = nullptr;
+    int* d_trace_cnt = nullptr;
+    int n_trace = 0, trace_max = 0;
+    std::vector<long long> trace_idx;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    long long* d_gather = nullptr;
+    McsTiming tm;
+    DevParams P;
+};
+
+static int pop_alloc(PopPtrs& p, long long n) {
+    size_t nd = (size_t)n;
+    CU(cudaMalloc(&p.weight, nd * 8)); CU(cudaMalloc(&p.ptot, nd * 8)); CU(cudaMalloc(&p.pb, nd * 8));
+    CU(cudaMalloc(&p.x, nd * 8)); CU(cudaMalloc(&p.xn_per, nd * 8)); CU(cudaMalloc(&p.prp_x, nd * 8));
+    CU(cudaMalloc(&p.acctime, nd * 8)); CU(cudaMalloc(&p.phi, nd * 8)); CU(cudaMalloc(&p.grid, nd * 8));
+    CU(cudaMalloc(&p.tcut, nd * 8)); CU(cudaMalloc(&p.down, nd)); CU(cudaMalloc(&p.inj, nd));
+    return MCS_OK;
+}
+static void pop_free(PopPtrs& p) {
+    cudaFree(p.weight); cudaFree(p.ptot); cudaFree(p.pb); cudaFree(p.x); cudaFree(p.xn_per); cudaFree(p.prp_x);
+    cudaFree(p.acctime); cudaFree(p.phi); cudaFree(p.grid); cudaFree(p.tcut); cudaFree(p.down); cudaFree(p.inj);
+    memset(&p, 0, sizeof p);
+}
+
+static size_t psd_len(const McsHandle* h) { return (size_t)(h->M + 2) * (size_t)(h->T + 2) * (size_t)h->ng; }
+
+extern "C" int mcs_destroy(McsHandle* h) {
+    if (!h) return MCS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->d_grid); cudaFree(h->d_zone);
+    for (auto& p : h->pop) pop_free(p);
+    cudaFree(h->d_l_save); cudaFree(h->d_fate); cudaFree(h->d_helix); cudaFree(h->d_retro); cudaFree(h->d_draws);
+    cudaFree(h->d_saved_idx); cudaFree(h->d_block_off); cudaFree(h->d_total); cudaFree(h->d_block_cnt);
+    cudaFree(h->d_tally); cudaFree(h->d_u64); cudaFree(h->d_tg); cudaFree(h->d_tpx); cudaFree(h->d_tpt); cudaFree(h->d_tw);
+    cudaFree(h->d_partials); cudaFree(h->d_replay_u); cudaFree(h->d_replay_off); cudaFree(h->d_trace_slot);
+    cudaFree(h->d_trace_recs); cudaFree(h->d_trace_cnt); cudaFree(h->d_gather);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MCS_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
+    if (!cfg || !out) return fail(MCS_ERR_ARG, "null argument");
+    if (cfg->abi_version != MCS_ABI_VERSION) return fail(MCS_ERR_ARG, "abi_version mismatch");
+    if (cfg->n_grid < 1 || cfg->n_grid > 1536 || cfg->n_pts_max < 1 || cfg->n_ions < 1 || cfg->n_ions > MCS_MAX_IONS ||
+        cfg->n_tcuts > MCS_NA_C || cfg->n_tcuts < 0 || cfg->n_xspec > MCS_MAX_XSPEC || cfg->n_xspec < 0 ||
+        cfg->num_psd_mom_bins < 1 || cfg->num_psd_theta_bins < 1 || cfg->na_cr < 0)
+        return fail(MCS_ERR_ARG, "bad sizes in McsConfig");
+    if (cfg->use_custom_frg) return fail(MCS_ERR_UNSUPPORTED, "use_custom_frg: the reference errors too (scattering.jl:53)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(MCS_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    int dev = cfg->device;
+    if (dev < 0) {
+        const char* lr = getenv("LOCAL_RANK");
+        dev = lr ? atoi(lr) % ndev : 0;
+    }
+    if (dev >= ndev) return fail(MCS_ERR_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(dev));
+    McsHandle* h = new McsHandle();
+    memset(&h->tm, 0, sizeof h->tm);
+    memset(h->pop, 0, sizeof h->pop);
+    memset(h->h_counters, 0, sizeof h->h_counters);
+    h->cfg = *cfg; h->device = dev;
+    h->ng = cfg->n_grid; h->M = cfg->num_psd_mom_bins; h->T = cfg->num_psd_theta_bins;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    h->n_sm = prop.multiProcessorCount;
+    h->block = env_int("MCS_BLOCK", 256);
+    h->blocks_per_sm = env_int("MCS_BLOCKS_PER_SM", 2);
+    h->max_blocks = h->n_sm * h->blocks_per_sm;
+    int rc = MCS_OK;
+#define TRY(x) do { rc = (x); if (rc != MCS_OK) { mcs_destroy(h); return rc; } } while (0)
+#define CUA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(MCS_ERR_NOMEM, "CUDA alloc: %s at %s", cudaGetErrorString(e_), #call); mcs_destroy(h); return MCS_ERR_NOMEM; } } while (0)
+    CUA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUA(cudaEventCreate(&h->ev0)); CUA(cudaEventCreate(&h->ev1)); CUA(cudaEventCreate(&h->ev2)); CUA(cudaEventCreate(&h->ev3));
+    const int ng = h->ng, ng2 = ng + 2;
+    const long long N = cfg->n_pts_max;
+    CUA(cudaMalloc(&h->d_grid, (size_t)(9 * ng2 + MCS_NA_C) * 8));
+    CUA(cudaMalloc(&h->d_zone, (size_t)2 * ng * 8));
+    for (auto& p : h->pop) TRY(pop_alloc(p, N));
+    CUA(cudaMalloc(&h->d_l_save, (size_t)N)); CUA(cudaMalloc(&h->d_fate, (size_t)N * 4)); CUA(cudaMalloc(&h->d_helix, (size_t)N * 4));
+    CUA(cudaMalloc(&h->d_retro, (size_t)N * 8)); CUA(cudaMalloc(&h->d_draws, (size_t)N * 8));
+    CUA(cudaMalloc(&h->d_saved_idx, (size_t)N * 8));
+    const int scan_blocks = (int)((N + 1023) / 1024);
+    CUA(cudaMalloc(&h->d_block_cnt, (size_t)scan_blocks * 4)); CUA(cudaMalloc(&h->d_block_off, (size_t)scan_blocks * 8));
+    CUA(cudaMalloc(&h->d_total, 8));
+    // packed FP64 tally buffer
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+    h->off_pxx = take(ng); h->off_pxz = take(ng); h->off_efl = take(ng); h->off_psd = take(psd_len(h));
+    h->off_esc_up = take((size_t)E1 * E1); h->off_esc_dn = take((size_t)E1 * E1); h->off_en_eff = take(E1);
+    h->off_num_eff = take(E1); h->off_wc = take(MCS_NA_C); h->off_sc = take((size_t)E1 * MCS_NA_C); h->off_pool = take(ng);
+    h->off_sf = take((size_t)E1 * MCS_MAX_XSPEC); h->off_pf = take((size_t)E1 * MCS_MAX_XSPEC); h->off_scal = take(SC_N);
+    h->n_tally = o;
+    CUA(cudaMalloc(&h->d_tally, o * 8));
+    CUA(cudaMalloc(&h->d_u64, (size_t)(ng + CNT_N) * 8));
+    const size_t L = (size_t)(cfg->na_cr > 0 ? cfg->na_cr : 1);
+    CUA(cudaMalloc(&h->d_tg, L * 8)); CUA(cudaMalloc(&h->d_tpx, L * 8)); CUA(cudaMalloc(&h->d_tpt, L * 8)); CUA(cudaMalloc(&h->d_tw, L * 8));
+    CUA(cudaMalloc(&h->d_partials, (size_t)h->max_blocks * 4 * ng * 8));
+    CUA(cudaMalloc(&h->d_gather, 64 * 8));
+    CUA(cudaMemsetAsync(h->d_tally, 0, o * 8, h->stream));
+    CUA(cudaMemsetAsync(h->d_u64, 0, (size_t)(ng + CNT_N) * 8, h->stream));
+    CUA(cudaFuncSetAttribute(transport_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ng * 8));
+    CUA(cudaFuncSetAttribute(transport_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ng * 8));
+#undef TRY
+#undef CUA
+    // static part of the kernel parameters
+    DevParams& P = h->P;
+    memset(&P, 0, sizeof P);
+    P.mp = cfg->mp_g; P.c = cfg->c_cms; P.qcgs = cfg->qcgs_esu; P.E_rel_pt = cfg->E_rel_pt; P.rad_loss_fac = cfg->rad_loss_fac;
+    P.gam0 = cfg->gam0; P.u0 = cfg->u0; P.u2 = cfg->u2; P.bmag2 = cfg->bmag2; P.pe_crit = cfg->pe_crit;
+    P.gam_e_crit = cfg->gam_e_crit; P.eta_mfp = cfg->eta_mfp;
+    P.psd_mom_min = cfg->psd_mom_min; P.psd_cos_fine = cfg->psd_cos_fine; P.delta_cos = cfg->delta_cos;
+    P.psd_theta_min = cfg->psd_theta_min; P.bpd_mom = (double)cfg->psd_bins_per_dec_mom; P.bpd_th = (double)cfg->psd_bins_per_dec_theta;
+    P.energy_transfer_frac = cfg->energy_transfer_frac; P.feb_up = cfg->feb_upstream; P.feb_dn = cfg->feb_downstream;
+    P.x_grid_stop = cfg->x_grid_stop; P.B_CMBz = cfg->B_CMBz; P.xn_fine = cfg->xn_per_fine; P.xn_coarse = cfg->xn_per_coarse;
+    P.age_max = cfg->age_max;
+    for (int i = 0; i < MCS_MAX_XSPEC; i++) P.x_spec[i] = cfg->x_spec[i];
+    P.M = h->M; P.T = h->T; P.n_grid = ng; P.i_grid_feb = cfg->i_grid_feb; P.i_shock = cfg->i_shock; P.n_xspec = cfg->n_xspec;
+    P.n_tcuts = cfg->n_tcuts; P.helix_cap = cfg->helix_cap; P.retro_cap = cfg->retro_cap;
+    P.flags = (cfg->do_rad_losses ? F_RAD_LOSSES : 0) | (cfg->do_retro ? F_RETRO : 0) | (cfg->do_tcuts ? F_TCUTS : 0) |
+              (cfg->dont_DSA ? F_DONT_DSA : 0) | (cfg->dont_scatter ? F_DONT_SCATTER : 0) |
+              (cfg->use_custom_epsB ? F_CUSTOM_EPSB : 0) | ((cfg->compat & MCS_COMPAT_RETRO_KEEP_NEW_PITCH) ? F_KEEP_NEW_PITCH : 0);
+    P.key0 = (uint32_t)cfg->seed; P.key1 = (uint32_t)(cfg->seed >> 32);
+    double* g = h->d_grid;
+    P.xg = g; P.ux = g + ng2; P.uz = g + 2 * ng2; P.ut = g + 3 * ng2; P.gsf = g + 4 * ng2; P.gef = g + 5 * ng2;
+    P.bt = g + 6 * ng2; P.sinth = g + 7 * ng2; P.costh = g + 8 * ng2; P.tcuts = g + 9 * ng2;
+    P.eps_target = h->d_zone; P.recv_pool = h->d_zone + ng;
+    P.l_save = h->d_l_save; P.fate = h->d_fate; P.helix = h->d_helix; P.retro = h->d_retro; P.draws = h->d_draws;
+    TallyPtrs& t = P.t;
+    double* b = h->d_tally;
+    t.psd = b + h->off_psd; t.esc_up = b + h->off_esc_up; t.esc_dn = b + h->off_esc_dn; t.esc_en_eff = b + h->off_en_eff;
+    t.esc_num_eff = b + h->off_num_eff; t.w_coupled = b + h->off_wc; t.s_coupled = b + h->off_sc; t.pool = b + h->off_pool;
+    t.spec_sf = b + h->off_sf; t.spec_pf = b + h->off_pf; t.scalars = b + h->off_scal;
+    t.counters = h->d_u64 + ng;
+    t.tg = h->d_tg; t.tpx = h->d_tpx; t.tpt = h->d_tpt; t.tw = h->d_tw; t.na_cr = cfg->na_cr;
+    t.block_partials = h->d_partials;
+    {
+        cudaError_t e2 = cudaMemcpyAsync((void*)P.tcuts, cfg->tcuts, MCS_NA_C * 8, cudaMemcpyHostToDevice, h->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(h->stream);
+        if (e2 != cudaSuccess) { mcs_destroy(h); return fail(MCS_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e2)); }
+    }
+    *out = h;
+    return MCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int mcs_comm_unique_id(void* id128) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NC(g_nccl.GetUniqueId((ncclUniqueId*)id128));
+    return MCS_OK;
+}
+extern "C" int mcs_comm_init(McsHandle* h, int rank, int nranks, const void* id128) {
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks || nranks > 64) return fail(MCS_ERR_ARG, "bad rank/nranks");
+    h->rank = rank; h->nranks = nranks;
+    if (nranks == 1) return MCS_OK;
+    if (!id128) return fail(MCS_ERR_ARG, "null unique id");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    return MCS_OK;
+}
+
+extern "C" int mcs_set_profile(McsHandle* h, int32_t n_grid, const double* xg, const double* ux, const double* uz,
+                               const double* ut, const double* gsf, const double* gef, const double* bef, const double* bt,
+                               const double* th, const double* eps_target, const double* recv_pool) {
+    (void)bef;
+    if (!h || n_grid != h->ng) return fail(MCS_ERR_ARG, "n_grid mismatch");
+    if (!xg || !ux || !uz || !ut || !gsf || !gef || !bt || !th) return fail(MCS_ERR_ARG, "null profile array");
+    CU(cudaSetDevice(h->device));
+    const int ng2 = h->ng + 2;
+    std::vector<double> buf((size_t)9 * ng2 + 2 * h->ng, 0.0);
+    const double* src[7] = {xg, ux, uz, ut, gsf, gef, bt};
+    for (int a = 0; a < 7; a++) memcpy(&buf[(size_t)a * ng2], src[a], (size_t)ng2 * 8);
+    for (int i = 0; i < ng2; i++) {  // per-zone sin/cos(theta_B) tables (particle_loop.jl:203-204), host libm
+        buf[(size_t)7 * ng2 + i] = sin(th[i]);
+        buf[(size_t)8 * ng2 + i] = cos(th[i]);
+    }
+    if (eps_target) memcpy(&buf[(size_t)9 * ng2], eps_target, (size_t)h->ng * 8);
+    if (recv_pool) memcpy(&buf[(size_t)9 * ng2 + h->ng], recv_pool, (size_t)h->ng * 8);
+    CU(cudaMemcpyAsync(h->d_grid, buf.data(), (size_t)9 * ng2 * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_zone, &buf[(size_t)9 * ng2], (size_t)2 * h->ng * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_profile = true;
+    return MCS_OK;
+}
+
+extern "C" int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies* sp, int64_t n, int64_t first_global,
+                             const McsPopulation* pop) {
+    if (!h || !sp || !pop) return fail(MCS_ERR_ARG, "null argument");
+    if (!h->have_profile) return fail(MCS_ERR_STATE, "mcs_set_profile first");
+    if (n < 0 || n > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "n_pts exceeds n_pts_max");
+    if (i_ion < 1 || i_ion > h->cfg.n_ions) return fail(MCS_ERR_ARG, "i_ion out of range");
+    if (n > 0 && (!pop->weight || !pop->ptot_pf || !pop->pb_pf || !pop->x_cm || !pop->grid || !pop->phi_rad))
+        return fail(MCS_ERR_ARG, "weight/ptot_pf/pb_pf/x_cm/grid/phi_rad are required");
+    for (int64_t i = 0; i < n; i++)
+        if (pop->grid[i] < 0 || pop->grid[i] > h->ng + 1) return fail(MCS_ERR_ARG, "grid index out of range");
+    CU(cudaSetDevice(h->device));
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion;
+    h->n_use = n; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
+    // clear_psd! (ion_init.jl:1-16) and every other per-ion sum
+    CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
+    CU(cudaMemsetAsync(h->d_u64, 0, (size_t)(h->ng + CNT_N) * 8, h->stream));
+    memset(h->h_counters, 0, sizeof h->h_counters);
+    CU(cudaEventRecord(h->ev2, h->stream));
+    PopPtrs& p = h->pop[h->cur];
+    size_t nb = (size_t)n * 8;
+#define UP(dst, src, bytes) do { if (src && n > 0) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream)); } while (0)
+    UP(p.weight, pop->weight, nb); UP(p.ptot, pop->ptot_pf, nb); UP(p.pb, pop->pb_pf, nb); UP(p.x, pop->x_cm, nb);
+    UP(p.phi, pop->phi_rad, nb); UP(p.grid, pop->grid, nb); UP(p.xn_per, pop->xn_per, nb); UP(p.prp_x, pop->prp_x_cm, nb);
+    UP(p.acctime, pop->acctime_sec, nb); UP(p.tcut, pop->tcut, nb); UP(p.down, pop->downstream, (size_t)n); UP(p.inj, pop->inj, (size_t)n);
+#undef UP
+    if (n > 0) {
+        fill_defaults_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+            p, n, pop->downstream != nullptr, pop->inj != nullptr, pop->xn_per != nullptr, pop->prp_x_cm != nullptr,
+            pop->acctime_sec != nullptr, pop->tcut != nullptr, h->cfg.xn_per_fine, h->cfg.x_grid_stop);
+        h->tm.other_launches++;
+    }
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    h->tm.h2d_ms += ms;
+    h->have_ion = true;
+    return MCS_OK;
+}
+
+static int read_counters(McsHandle* h) {
+    CU(cudaMemcpyAsync(h->h_counters, h->d_u64 + h->ng, CNT_N * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MCS_OK;
+}
+
+extern "C" int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_prev, int64_t* n_saved, int64_t* n_steps) {
+    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    CU(cudaSetDevice(h->device));
+    const long long n = h->n_use;
+    const unsigned long long steps0 = h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO];
+    const unsigned long long saved0 = h->h_counters[CNT_FATE0];
+    DevParams& P = h->P;
+    P.aa = h->sp.aa; P.zz = h->sp.zz_esu; P.n0 = h->sp.n0; P.pmax_cutoff = h->sp.pmax_cutoff; P.ewf = h->sp.electron_weight_fac;
+    P.m = P.aa * P.mp; P.mc = P.m * P.c; P.inj_frac = h->cfg.inj_fracs[h->i_ion - 1];
+    P.pcut = pcut; P.pcut_prev = pcut_prev;
+    P.ctr2 = ((uint32_t)i_pcut & 0xFFFFu) | ((uint32_t)h->i_ion << 16); P.ctr3 = (uint32_t)h->i_iter;
+    P.first_global = h->first_global; P.n_use = n;
+    P.cur = h->pop[h->cur]; P.saved = h->pop[1];
+    const bool debug = h->cfg.rng_mode == MCS_RNG_REPLAY || h->n_trace > 0;
+    P.replay_u = h->cfg.rng_mode == MCS_RNG_REPLAY ? h->d_replay_u : nullptr;
+    P.replay_off = h->d_replay_off; P.replay_n = h->replay_n;
+    if (h->cfg.rng_mode == MCS_RNG_REPLAY && !h->d_replay_u) return fail(MCS_ERR_STATE, "replay mode without mcs_replay_set_stream");
+    P.trace_slot = nullptr; P.trace_recs = h->d_trace_recs; P.trace_cnt = h->d_trace_cnt; P.trace_max = h->trace_max;
+    if (h->n_trace > 0 && n > 0) {
+        std::vector<int> slot((size_t)n, -1);
+        for (int t = 0; t < h->n_trace; t++)
+            if (h->trace_idx[t] >= 0 && h->trace_idx[t] < n) slot[(size_t)h->trace_idx[t]] = t;
+        cudaFree(h->d_trace_slot); h->d_trace_slot = nullptr;
+        CU(cudaMalloc(&h->d_trace_slot, (size_t)n * 4));
+        CU(cudaMemcpyAsync(h->d_trace_slot, slot.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_trace_cnt, 0, (size_t)h->n_trace * 4, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        P.trace_slot = h->d_trace_slot;
+    }
+    // l_save .= false (main_loops.jl:184); the *_saved arrays are only read where l_save is set
+    CU(cudaMemsetAsync(h->d_l_save, 0, (size_t)(n > 0 ? n : 1), h->stream));
+    CU(cudaMemsetAsync(h->d_u64 + h->ng + CNT_QUEUE, 0, 8, h->stream));
+    if (n > 0) {
+        long long want = (n + h->block - 1) / h->block;
+        int blocks = (int)(want < h->max_blocks ? want : h->max_blocks);
+        size_t smem = (size_t)4 * h->ng * 8;
+        CU(cudaEventRecord(h->ev0, h->stream));
+        if (debug) transport_kernel<true><<<blocks, h->block, smem, h->stream>>>(P);
+        else transport_kernel<false><<<blocks, h->block, smem, h->stream>>>(P);
+        CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaGetLastError());
+        double* b = h->d_tally;
+        reduce_partials_kernel<<<(4 * h->ng + 127) / 128, 128, 0, h->stream>>>(h->d_partials, blocks, h->ng, b + h->off_pxx,
+                                                                             b + h->off_pxz, b + h->off_efl, h->d_u64);
+        CU(cudaGetLastError());
+        h->tm.transport_launches++; h->tm.other_launches++;
+    }
+    int rc = read_counters(h);
+    if (rc) return rc;
+    if (n > 0) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->tm.transport_ms += ms;
+    }
+    h->n_saved_last = (long long)(h->h_counters[CNT_FATE0] - saved0);
+    if (n_saved) *n_saved = h->n_saved_last;
+    if (n_steps) *n_steps = (int64_t)(h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO] - steps0);
+    return MCS_OK;
+}
+
+extern "C" int mcs_split_explicit(McsHandle* h, int64_t i_mult, int64_t first_global_child, int64_t* n_new_local) {
+    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    if (i_mult < 1) return fail(MCS_ERR_ARG, "i_mult < 1");
+    const long long n = h->n_use, ns = h->n_saved_last, n_out = ns * i_mult;
+    if (n_out > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "split population exceeds n_pts_max");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev2, h->stream));
+    if (ns > 0) {
+        const int nb = (int)((n + 1023) / 1024);
+        count_saved_kernel<<<nb, 1024, 0, h->stream>>>(h->d_l_save, n, h->d_block_cnt);
+        scan_blocks_kernel<<<1, 1024, 0, h->stream>>>(h->d_block_cnt, nb, h->d_block_off, h->d_total);
+        compact_saved_kernel<<<nb, 1024, 0, h->stream>>>(h->d_l_save, n, h->d_block_off, h->d_saved_idx);
+        clone_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, h->stream>>>(h->pop[1], h->pop[h->nxt], h->d_saved_idx, n_out, i_mult);
+        CU(cudaGetLastError());
+        h->tm.other_launches += 4;
+    }
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    h->tm.split_ms += ms;
+    int t = h->cur; h->cur = h->nxt; h->nxt = t;
+    h->n_use = n_out; h->first_global = first_global_child;
+    if (n_new_local) *n_new_local = n_out;
+    return MCS_OK;
+}
+
+extern "C" int mcs_split(McsHandle* h, int64_t n_pts_target, int64_t* n_new_local, int64_t* n_new_global, int64_t* i_mult_out) {
+    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    long long ns_global = h->n_saved_last, lower = 0;
+    if (h->nranks > 1) {  // one all-gather of the per-rank n_saved
+        CU(cudaSetDevice(h->device));
+        long long v = h->n_saved_last;
+        long long all[64];
+        CU(cudaEventRecord(h->ev2, h->stream));
+        CU(cudaMemcpyAsync(h->d_gather + h->rank, &v, 8, cudaMemcpyHostToDevice, h->stream));
+        NC(g_nccl.AllGather(h->d_gather + h->rank, h->d_gather, 1, ncclInt64, h->comm, h->stream));
+        CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->ev3, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        h->tm.comm_ms += ms;
+        ns_global = 0;
+        for (int r = 0; r < h->nranks; r++) { ns_global += all[r]; if (r < h->rank) lower += all[r]; }
+    }
+    h->n_saved_global_last = ns_global;
+    if (ns_global <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
+    long long i_mult = n_pts_target / ns_global;  // cuts.jl:42
+    if (i_mult < 1) i_mult = 1;
+    int64_t k = 0;
+    int rc = mcs_split_explicit(h, i_mult, i_mult * lower, &k);
+    if (rc) return rc;
+    if (n_new_local) *n_new_local = k;
+    if (n_new_global) *n_new_global = ns_global * i_mult;
+    if (i_mult_out) *i_mult_out = i_mult;
+    return MCS_OK;
+}
+
+static int global_sum_ll(McsHandle* h, long long v, long long* out) {
+    if (h->nranks == 1) { *out = v; return MCS_OK; }
+    long long all[64];
+    CU(cudaMemcpyAsync(h->d_gather + h->rank, &v, 8, cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(h->d_gather + h->rank, h->d_gather, 1, ncclInt64, h->comm, h->stream));
+    CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    long long s = 0;
+    for (int r = 0; r < h->nranks; r++) s += all[r];
+    *out = s;
+    return MCS_OK;
+}
+
+extern "C" int mcs_run_ion(McsHandle* h, const double* pcuts, int32_t n_pcuts, double p_pcut_hi, int64_t n_pts_pcut,
+                           int64_t n_pts_pcut_hi, int32_t* n_run, int64_t* n_used, int64_t* n_saved_arr) {
+    if (!h || !pcuts || n_pcuts < 1 || n_pcuts > MCS_NA_C) return fail(MCS_ERR_ARG, "bad pcuts");
+    int32_t k = 0;
+    for (int32_t i = 1; i <= n_pcuts; i++) {
+        int64_t ns = 0, nst = 0;
+        long long used_g = 0;
+        int rc = global_sum_ll(h, h->n_use, &used_g);
+        if (rc) return rc;
+        if (n_used) n_used[i - 1] = used_g;
+        rc = mcs_run_pcut(h, i, pcuts[i - 1], i > 1 ? pcuts[i - 2] : 0.0, &ns, &nst);
+        if (rc) return rc;
+        k = i;
+        int64_t target = pcuts[i - 1] < p_pcut_hi ? n_pts_pcut : n_pts_pcut_hi;
+        if (h->nranks == 1) {
+            if (n_saved_arr) n_saved_arr[i - 1] = ns;
+            if (ns == 0) break;  // pcut_finalize: break_pcut
+            rc = mcs_split(h, target, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+        } else {
+            // every rank must take the same branch: decide on the global count
+            long long ns_g = 0;
+            rc = global_sum_ll(h, ns, &ns_g);
+            if (rc) return rc;
+            if (n_saved_arr) n_saved_arr[i - 1] = ns_g;
+            if (ns_g == 0) break;
+            rc = mcs_split(h, target, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+        }
+    }
+    if (n_run) *n_run = k;
+    return MCS_OK;
+}
+
+extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
+    if (!h || !t) return fail(MCS_ERR_ARG, "null argument");
+    if (!h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    CU(cudaSetDevice(h->device));
+    // thermal log count is rank-local: read it before the counters are summed over ranks
+    int rc = read_counters(h);
+    if (rc) return rc;
+    const long long log_claimed = (long long)h->h_counters[CNT_LOG];
+    const long long n_log = log_claimed < h->cfg.na_cr ? log_claimed : h->cfg.na_cr;
+    if (h->nranks > 1) {  // ONE all-reduce over the packed FP64 tallies (+ one for the integer counts)
+        CU(cudaEventRecord(h->ev2, h->stream));
+        NC(g_nccl.AllReduce(h->d_tally, h->d_tally, h->n_tally, ncclFloat64, ncclSum, h->comm, h->stream));
+        NC(g_nccl.AllReduce(h->d_u64, h->d_u64, (size_t)(h->ng + CNT_N), ncclUint64, ncclSum, h->comm, h->stream));
+        CU(cudaEventRecord(h->ev3, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        h->tm.comm_ms += ms;
+        rc = read_counters(h);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(h->ev2, h->stream));
+    const size_t ng = (size_t)h->ng;
+    double* b = h->d_tally;
+#define DN(dst, src, count) do { if (dst && (count) > 0) CU(cudaMemcpyAsync(dst, src, (size_t)(count) * 8, cudaMemcpyDeviceToHost, h->stream)); } while (0)
+    DN(t->pxx_flux, b + h->off_pxx, ng); DN(t->pxz_flux, b + h->off_pxz, ng); DN(t->energy_flux, b + h->off_efl, ng);
+    DN(t->psd, b + h->off_psd, psd_len(h)); DN(t->num_crossings, h->d_u64, ng);
+    DN(t->therm_grid, h->d_tg, n_log); DN(t->therm_px_sk, h->d_tpx, n_log); DN(t->therm_ptot_sk, h->d_tpt, n_log);
+    DN(t->therm_weight, h->d_tw, n_log);
+    DN(t->esc_psd_feb_upstream, b + h->off_esc_up, (size_t)E1 * E1); DN(t->esc_psd_feb_downstream, b + h->off_esc_dn, (size_t)E1 * E1);
+    DN(t->esc_energy_eff, b + h->off_en_eff, E1); DN(t->esc_num_eff, b + h->off_num_eff, E1);
+    DN(t->weight_coupled, b + h->off_wc, MCS_NA_C); DN(t->spectra_coupled, b + h->off_sc, (size_t)E1 * MCS_NA_C);
+    DN(t->energy_transfer_pool, b + h->off_pool, ng);
+    DN(t->spectra_sf, b + h->off_sf, (size_t)E1 * h->cfg.n_xspec); DN(t->spectra_pf, b + h->off_pf, (size_t)E1 * h->cfg.n_xspec);
+    double sc[SC_N];
+    CU(cudaMemcpyAsync(sc, b + h->off_scal, SC_N * 8, cudaMemcpyDeviceToHost, h->stream));
+#undef DN
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    h->tm.d2h_ms += ms;
+    t->n_cr_count = n_log; t->n_cr_overflow = log_claimed - n_log;
+    t->esc_flux = sc[SC_ESC_FLUX]; t->px_esc_feb = sc[SC_PX_ESC_FEB]; t->energy_esc_feb = sc[SC_EN_ESC_FEB];
+    t->sum_P_downstream = sc[SC_SUMP]; t->sum_KE_downstream = sc[SC_SUMKE];
+    t->px_esc_upstream = sc[SC_PX_ESC_UP]; t->energy_esc_upstream = sc[SC_EN_ESC_UP];
+    const unsigned long long* c = h->h_counters;
+    t->n_helix_steps = (int64_t)c[CNT_HELIX]; t->n_retro_steps = (int64_t)c[CNT_RETRO];
+    t->n_warn_pperp = (int64_t)c[CNT_W_PPERP]; t->n_warn_psd_mom = (int64_t)c[CNT_W_PSDMOM]; t->n_neg_sqrt = (int64_t)c[CNT_NEGSQRT];
+    t->n_retro_capped = (int64_t)c[CNT_RETRO_CAP]; t->n_errors = (int64_t)c[CNT_ERR];
+    for (int i = 0; i < 6; i++) t->n_fate[i] = (int64_t)c[CNT_FATE0 + i];
+    return MCS_OK;
+}
+
+extern "C" int mcs_get_population(McsHandle* h, int32_t which, int64_t n, McsPopulation* o, uint8_t* l_save) {
+    if (!h || !o) return fail(MCS_ERR_ARG, "null argument");
+    if (n < 0 || n > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "n out of range");
+    CU(cudaSetDevice(h->device));
+    PopPtrs& p = which == 0 ? h->pop[h->cur] : h->pop[1];
+    size_t nb = (size_t)n * 8;
+#define DN(dst, src, bytes) do { if (dst && n > 0) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream)); } while (0)
+    DN(o->weight, p.weight, nb); DN(o->ptot_pf, p.ptot, nb); DN(o->pb_pf, p.pb, nb); DN(o->x_cm, p.x, nb);
+    DN(o->xn_per, p.xn_per, nb); DN(o->prp_x_cm, p.prp_x, nb); DN(o->acctime_sec, p.acctime, nb); DN(o->phi_rad, p.phi, nb);
+    DN(o->grid, p.grid, nb); DN(o->tcut, p.tcut, nb); DN(o->downstream, p.down, (size_t)n); DN(o->inj, p.inj, (size_t)n);
+    DN(l_save, h->d_l_save, (size_t)n);
+#undef DN
+    CU(cudaStreamSynchronize(h->stream));
+    if (which == 1 && l_save) {  // reference zeroes the *_saved arrays (main_loops.jl:186-197): mask unsaved slots
+        for (int64_t i = 0; i < n; i++) {
+            if (l_save[i]) continue;
+            if (o->weight) o->weight[i] = 0; if (o->ptot_pf) o->ptot_pf[i] = 0; if (o->pb_pf) o->pb_pf[i] = 0;
+            if (o->x_cm) o->x_cm[i] = 0; if (o->xn_per) o->xn_per[i] = 0; if (o->prp_x_cm) o->prp_x_cm[i] = 0;
+            if (o->acctime_sec) o->acctime_sec[i] = 0; if (o->phi_rad) o->phi_rad[i] = 0; if (o->grid) o->grid[i] = 0;
+            if (o->tcut) o->tcut[i] = 0; if (o->downstream) o->downstream[i] = 0; if (o->inj) o->inj[i] = 0;
+        }
+    }
+    return MCS_OK;
+}
+extern "C" int64_t mcs_population_size(McsHandle* h) { return h ? h->n_use : -1; }
+
+extern "C" int mcs_get_fates(McsHandle* h, int64_t n, int32_t* fate, int32_t* helix, int64_t* retro, int64_t* draws) {
+    if (!h || n < 0 || n > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    if (n > 0) {
+        if (fate) CU(cudaMemcpyAsync(fate, h->d_fate, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (helix) CU(cudaMemcpyAsync(helix, h->d_helix, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (retro) CU(cudaMemcpyAsync(retro, h->d_retro, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (draws) CU(cudaMemcpyAsync(draws, h->d_draws, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return MCS_OK;
+}
+
+extern "C" int mcs_replay_set_stream(McsHandle* h, const double* u, const int64_t* off, int64_t n) {
+    if (!h || !u || !off || n < 0) return fail(MCS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    cudaFree(h->d_replay_u); cudaFree(h->d_replay_off);
+    h->d_replay_u = nullptr; h->d_replay_off = nullptr;
+    const int64_t tot = off[n];
+    CU(cudaMalloc(&h->d_replay_u, (size_t)(tot > 0 ? tot : 1) * 8));
+    CU(cudaMalloc(&h->d_replay_off, (size_t)(n + 1) * 8));
+    CU(cudaMemcpyAsync(h->d_replay_u, u, (size_t)tot * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_replay_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->replay_n = n;
+    return MCS_OK;
+}
+
+extern "C" int mcs_trace_enable(McsHandle* h, const int64_t* idx, int32_t n_trace, int32_t max_steps) {
+    if (!h || n_trace < 0 || max_steps < 0) return fail(MCS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    cudaFree(h->d_trace_recs); cudaFree(h->d_trace_cnt);
+    h->d_trace_recs = nullptr; h->d_trace_cnt = nullptr;
+    h->n_trace = n_trace; h->trace_max = max_steps;
+    h->trace_idx.assign(idx, idx + n_trace);
+    if (n_trace == 0) return MCS_OK;
+    CU(cudaMalloc(&h->d_trace_recs, (size_t)n_trace * (size_t)(max_steps > 0 ? max_steps : 1) * sizeof(McsTraceRec)));
+    CU(cudaMalloc(&h->d_trace_cnt, (size_t)n_trace * 4));
+    CU(cudaMemset(h->d_trace_cnt, 0, (size_t)n_trace * 4));
+    return MCS_OK;
+}
+extern "C" int mcs_trace_get(McsHandle* h, McsTraceRec* recs, int32_t* n_rec) {
+    if (!h || !h->n_trace) return fail(MCS_ERR_STATE, "trace not enabled");
+    CU(cudaSetDevice(h->device));
+    if (recs) CU(cudaMemcpy(recs, h->d_trace_recs, (size_t)h->n_trace * h->trace_max * sizeof(McsTraceRec), cudaMemcpyDeviceToHost));
+    if (n_rec) CU(cudaMemcpy(n_rec, h->d_trace_cnt, (size_t)h->n_trace * 4, cudaMemcpyDeviceToHost));
+    return MCS_OK;
+}
+
+extern "C" int mcs_get_timing(McsHandle* h, McsTiming* out, int32_t reset) {
+    if (!h) return fail(MCS_ERR_ARG, "null handle");
+    if (out) *out = h->tm;
+    if (reset) memset(&h->tm, 0, sizeof h->tm);
+    return MCS_OK;
+}
+
+extern "C" int mcs_measure_fp64_peak(McsHandle* h, double* tflops) {
+    if (!h || !tflops) return fail(MCS_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int blocks = h->n_sm * 8, threads = 256, iters = 1 << 15;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)blocks * threads * 8));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(h->ev2, h->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters);
+        CU(cudaEventRecord(h->ev3, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaFree(d);
+    *tflops = best;
+    return MCS_OK;
+}
+
+extern "C" int mcs_measure_atomic_peak(McsHandle* h, int64_t n_cells, double* gops) {
+    if (!h || !gops || n_cells < 1) return fail(MCS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    const int blocks = h->n_sm * 8, threads = 256, iters = 2048;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)n_cells * 8));
+    CU(cudaMemset(d, 0, (size_t)n_cells * 8));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(h->ev2, h->stream));
+        atomic_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, n_cells, iters);
+        CU(cudaEventRecord(h->ev3, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        double g = (double)iters * blocks * threads / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaFree(d);
+    *gops = best;
+    return MCS_OK;
+}

@@ -1,0 +1,905 @@
+// mcs_device.cuh — device side of the B200 transport loop (sm_100a).
+//
+// One persistent kernel advances a whole pcut's population: every lane owns one particle at a time,
+// runs helix-loop passes (reference src/particle_loop.jl:154-499) until the particle is saved, escapes
+// or is lost, tallies it (src/particle_finish.jl:46-107) and claims the next particle from a global
+// queue with one warp-aggregated atomic per refill.  Nothing returns to the host within a pcut.
+//
+// This is FP64 scalar work with data-dependent control flow: no dense contraction, so no tensor
+// cores / TMA; the levers are FP64-pipe issue efficiency, warp occupancy of the lanes (refill), and
+// where the tallies live (shared memory per block for the n_grid-sized flux arrays, L2 atomics for the
+// 22 MB phase-space histogram).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mcs.h"
+
+namespace mcs {
+
+constexpr double PI = 3.141592653589793;
+constexpr double TWO_PI = 6.283185307179586;
+constexpr double TWO_PI_LO = 2.4492935982947064e-16;
+constexpr double HALF_PI = PI / 2;
+constexpr double SIN_UPPER_LIMIT = 0.99999999999999989;  // prevfloat(1.0), scattering.jl:3
+constexpr double SPIKE_AWAY = 1000.0;                    // all_flux.jl:4, particle_finish.jl:5
+constexpr int E1 = MCS_PSD_MAX + 1;
+
+enum : uint32_t {
+    F_RAD_LOSSES = 1u, F_RETRO = 2u, F_TCUTS = 4u, F_DONT_DSA = 8u, F_DONT_SCATTER = 16u, F_CUSTOM_EPSB = 32u,
+    F_KEEP_NEW_PITCH = 64u,
+};
+
+// SoA particle record (main_loops.jl:212-226)
+struct PopPtrs {
+    double *weight, *ptot, *pb, *x, *xn_per, *prp_x, *acctime, *phi;
+    long long *grid, *tcut;
+    uint8_t *down, *inj;
+};
+
+struct TallyPtrs {
+    double* psd;            // [(M+2)(T+2) n_grid]
+    double* esc_up;         // [E1*E1]
+    double* esc_dn;         // [E1*E1]
+    double* esc_en_eff;     // [E1]
+    double* esc_num_eff;    // [E1]
+    double* w_coupled;      // [NA_C]
+    double* s_coupled;      // [E1*NA_C]
+    double* pool;           // [n_grid]
+    double* spec_sf;        // [E1*MAX_XSPEC]
+    double* spec_pf;
+    double* scalars;        // [8]: esc_flux, px_esc_feb, en_esc_feb, sumP, sumKE, px_esc_up, en_esc_up
+    unsigned long long* counters;  // [16] see CNT_*
+    // thermal-crossing log
+    long long* tg;
+    double *tpx, *tpt, *tw;
+    long long na_cr;
+    // per-block partials of the n_grid-sized tallies: [gridDim.x][4*n_grid] (pxx, pxz, efl, crossings-as-bits)
+    double* block_partials;
+};
+
+enum { SC_ESC_FLUX = 0, SC_PX_ESC_FEB, SC_EN_ESC_FEB, SC_SUMP, SC_SUMKE, SC_PX_ESC_UP, SC_EN_ESC_UP, SC_N = 8 };
+enum {
+    CNT_HELIX = 0, CNT_RETRO, CNT_W_PPERP, CNT_W_PSDMOM, CNT_NEGSQRT, CNT_RETRO_CAP, CNT_ERR, CNT_FATE0,  // ..FATE5 = 12
+    CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_N = 24
+};
+
+struct DevParams {
+    // constants / shock scalars
+    double mp, c, qcgs, E_rel_pt, rad_loss_fac, gam0, u0, u2, bmag2, pe_crit, gam_e_crit, eta_mfp;
+    double psd_mom_min, psd_cos_fine, delta_cos, psd_theta_min, bpd_mom, bpd_th;
+    double energy_transfer_frac, feb_up, feb_dn, x_grid_stop, B_CMBz, xn_fine, xn_coarse, age_max;
+    double x_spec[MCS_MAX_XSPEC];
+    int M, T, n_grid, i_grid_feb, i_shock, n_xspec, n_tcuts, helix_cap;
+    long long retro_cap;
+    uint32_t flags;
+    // species
+    double aa, zz, n0, pmax_cutoff, ewf, m, mc, inj_frac;
+    // current pcut
+    double pcut, pcut_prev;
+    uint32_t key0, key1, ctr2, ctr3;
+    long long first_global, n_use;
+    // grid arrays (n_grid+2) and per-zone tables
+    const double *xg, *ux, *uz, *ut, *gsf, *gef, *bt, *sinth, *costh, *tcuts;
+    const double *eps_target, *recv_pool;  // [n_grid]
+    PopPtrs cur, saved;
+    uint8_t* l_save;
+    int *fate, *helix;
+    long long *retro, *draws;
+    TallyPtrs t;
+    // debug: replay stream + trajectory trace
+    const double* replay_u;
+    const long long* replay_off;
+    long long replay_n;
+    const int* trace_slot;  // [n_use] or null
+    McsTraceRec* trace_recs;
+    int* trace_cnt;
+    int trace_max;
+};
+
+// ---------------------------------------------------------------------------------------------
+// RNG: Philox4x32-10, counter = (block, i_prt, i_pcut | i_ion<<16, i_iter), key = seed. Replaces the
+// per-particle Random.Xoshiro(iseed_mod) of particle_loop.jl:34-41.  Integer pipe only.
+struct Rng {
+    uint32_t n, s2, s3, c1;
+    const double* ru;
+    long long rn;
+    bool exhausted;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return __ull2double_rn((((unsigned long long)hi << 32) | lo) >> 11) * 0x1.0p-53;
+}
+
+template <bool DEBUG>
+__device__ __forceinline__ double uniform(Rng& g, const DevParams& P) {
+    if (DEBUG && g.ru != nullptr) {
+        if ((long long)g.n >= g.rn) { g.exhausted = true; g.n++; return 0.5; }
+        return g.ru[g.n++];
+    }
+    uint32_t k = g.n++;
+    if ((k & 1u) == 0u) {
+        uint32_t o0, o1, o2, o3;
+        philox4x32_10(k >> 1, g.c1, P.ctr2, P.ctr3, P.key0, P.key1, o0, o1, o2, o3);
+        g.s2 = o2; g.s3 = o3;
+        return u53(o1, o0);
+    }
+    return u53(g.s3, g.s2);
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mod2pi(double x) {  // Base.mod2pi semantics
+    if (x >= 0.0 && x < TWO_PI) return x;
+    double k = floor(x / TWO_PI);
+    double r = fma(-k, TWO_PI, x);
+    r = r - k * TWO_PI_LO;
+    if (r < 0.0) r += TWO_PI;
+    if (r >= TWO_PI) r -= TWO_PI;
+    return r;
+}
+
+__device__ __forceinline__ double norm3(double x, double y, double z) {
+    double s = x * x + y * y + z * z;
+    if (s == 0.0 || isinf(s)) {
+        double m = fmax(fabs(x), fmax(fabs(y), fabs(z)));
+        if (m == 0.0 || isinf(m)) return m;
+        double a = x / m, b = y / m, c = z / m;
+        return m * sqrt(a * a + b * b + c * c);
+    }
+    return sqrt(s);
+}
+
+__device__ __forceinline__ void count(const DevParams& P, int which, unsigned long long v = 1ull) {
+    atomicAdd(&P.t.counters[which], v);
+}
+
+__device__ __forceinline__ double sqrt_guard(const DevParams& P, double a) {
+    if (a < 0.0) { count(P, CNT_NEGSQRT); return 0.0; }
+    return sqrt(a);
+}
+
+// get_psd_bins.jl:16-39
+__device__ __forceinline__ int psd_bin_momentum(const DevParams& P, double ptot_sk) {
+    int bin;
+    if (ptot_sk < P.psd_mom_min) bin = 0;
+    else bin = (int)trunc(log10(ptot_sk / P.psd_mom_min) * P.bpd_mom) + 1;
+    if (bin > P.M) { count(P, CNT_W_PSDMOM); bin = P.M; }
+    return bin;
+}
+// get_psd_bins.jl:73-97
+__device__ __forceinline__ int psd_bin_angle(const DevParams& P, double px_sk, double ptot_sk) {
+    if (ptot_sk == 0.0) return 0;
+    double p_cos = -px_sk / ptot_sk;
+    int bin;
+    if (p_cos < P.psd_cos_fine) {
+        bin = P.T - (int)trunc((p_cos + 1) / P.delta_cos);
+    } else {
+        double th = acos(p_cos);
+        bin = th < P.psd_theta_min ? 0 : (int)trunc(log10(th / P.psd_theta_min) * P.bpd_th) + 1;
+    }
+    return min(bin, P.T);
+}
+
+// transformers.jl:440-476 (uz, utot do not enter the parallel-to-x boost as written)
+__device__ __forceinline__ void transform_p_PS(const DevParams& P, double pb, double pperp, double gam_pf, double phi,
+                                               double ux, double gsf, double bcos, double bsin, double& ptot_sk,
+                                               double& sx, double& sz, double& gam_sk) {
+    double sp, cp;
+    sincos(phi + HALF_PI, &sp, &cp);
+    double p_p_cos = pperp * cp;
+    double fx = pb * bcos - p_p_cos * bsin;
+    double fy = pperp * sp;
+    double fz = pb * bsin + p_p_cos * bcos;
+    double dpx = (gsf - 1) * fx + gsf * gam_pf * P.m * ux;
+    sx = fx + dpx;
+    sz = fz;
+    ptot_sk = norm3(sx, fy, sz);
+    gam_sk = hypot(ptot_sk / P.mc, 1.0);
+}
+
+// transformers.jl:523-607; zone `io` -> shock frame -> zone `in`
+__device__ __noinline__ void transform_p_PSP(const DevParams& P, int io, int in, double& ptot, double& pb,
+                                             double& pperp, double& gam_pf, double& phi) {
+    double ux_o = P.ux[io], uz_o = P.uz[io], ut_o = P.ut[io], gsf_o = P.gsf[io], bcos_o = P.costh[io],
+           bsin_o = P.sinth[io];
+    double ux = P.ux[in], uz = P.uz[in], ut = P.ut[in], gsf = P.gsf[in], bcos = P.costh[in], bsin = P.sinth[in];
+    double sp, cp;
+    sincos(phi + HALF_PI, &sp, &cp);
+    double p_p_cos = pperp * cp;
+    double fx = pb * bcos_o - p_p_cos * bsin_o;
+    double fy = pperp * sp;
+    double fz = pb * bsin_o + p_p_cos * bcos_o;
+    double rxo = ux_o / ut_o, rzo = uz_o / ut_o, cro = ux_o * uz_o / (ut_o * ut_o);
+    double sx = ((gsf_o - 1) * (rxo * rxo) + 1) * fx + (gsf_o - 1) * cro * fz + gsf_o * gam_pf * P.m * ux_o;
+    double sy = fy;
+    double sz = (gsf_o - 1) * cro * fx + ((gsf_o - 1) * (rzo * rzo) + 1) * fz + gsf_o * gam_pf * P.m * uz_o;
+    double ptot_sk = norm3(sx, sy, sz);
+    double pb_sk = sx * bcos + sz * bsin;
+    if (ptot_sk < fabs(pb_sk)) count(P, CNT_W_PPERP);
+    double gam_sk = hypot(ptot_sk / P.mc, 1.0);
+    double rx = ux / ut, rz = uz / ut, cr = ux * uz / (ut * ut);
+    double nx = ((gsf - 1) * (rx * rx) + 1) * sx + (gsf - 1) * cr * sz - gsf * gam_sk * P.m * ux;
+    double ny = sy;
+    double nz = (gsf - 1) * cr * sx + ((gsf - 1) * (rz * rz) + 1) * sz - gsf * gam_sk * P.m * uz;
+    double pt = norm3(nx, ny, nz);
+    double b = nx * bcos + nz * bsin, pp;
+    if (pt < fabs(b)) {
+        pp = 1.0e-6 * pt;
+        b = copysign(sqrt(pt * pt - pp * pp), b);
+        count(P, CNT_W_PPERP);
+    } else {
+        pp = sqrt(pt * pt - b * b);
+    }
+    ptot = pt; pb = b; pperp = pp;
+    gam_pf = hypot(pt / P.mc, 1.0);
+    phi = atan2(ny, -nx * bsin + nz * bcos) - HALF_PI;
+}
+
+__device__ __forceinline__ double perpendicular_momentum(const DevParams& P, double ptot, double pb) {
+    if (ptot < fabs(pb)) { count(P, CNT_W_PPERP); return 1.0e-6 * ptot; }
+    return sqrt(ptot * ptot - pb * pb);
+}
+
+__device__ __forceinline__ double radiation_loss(const DevParams& P, double B2, double p, double dt) {
+    double d = P.rad_loss_fac * B2 * p * dt;
+    return d > 1.0e-2 ? p / (1 + d) : p * (1 - d);
+}
+
+// cuts.jl:149-162
+__device__ __noinline__ void tcut_track(const DevParams& P, int tcut_curr, double weight, double ptot) {
+    atomicAdd(&P.t.w_coupled[tcut_curr - 1], weight);
+    int ip = psd_bin_momentum(P, ptot);
+    atomicAdd(&P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
+}
+
+// particle_loop.jl:652-723
+__device__ __noinline__ void do_energy_transfer(const DevParams& P, int i_grid, int i_grid_old, double& ptot,
+                                                double& pb, double& pperp, double& gam_pf, double weight) {
+    int i_start = i_grid_old, i_stop = min(i_grid, P.i_shock);
+    double E0 = P.m * (P.c * P.c), gam_f = 0.0;
+    bool scale = false;
+    double emax = -1.0, rmax = 0.0;  // F-11: empty range == nothing to do
+    for (int i = i_start + 1; i <= i_stop; i++) {
+        emax = fmax(emax, P.eps_target[i - 1]);
+        rmax = fmax(rmax, P.recv_pool[i - 1]);
+    }
+    if (P.aa >= 1 && i_start + 1 <= i_stop && emax > 0) {
+        double gam_i = hypot(1.0, ptot / P.mc);
+        double eps_start = i_start >= 1 ? P.eps_target[i_start - 1] : 0.0;
+        gam_f = 1 + (gam_i - 1) * (1 - P.eps_target[i_stop - 1]) / (1 - eps_start);
+        int n_split = 0;
+        for (int i = i_start + 1; i <= i_stop; i++) n_split += P.eps_target[i - 1] > 0;
+        double inc = (gam_i - gam_f) * E0 * weight / n_split;
+        for (int i = i_start + 1; i <= i_stop; i++)
+            if (P.eps_target[i - 1] > 0) atomicAdd(&P.t.pool[i - 1], inc);
+        scale = true;
+    } else if (rmax > 0) {
+        double sum = 0.0;
+        for (int i = i_start + 1; i <= i_stop; i++) sum += P.recv_pool[i - 1];
+        double gam_i = hypot(1.0, ptot / P.mc);
+        gam_f = gam_i + sum * P.ewf / E0;
+        scale = true;
+    }
+    if (scale) {
+        double pf = P.mc * sqrt_guard(P, gam_f * gam_f - 1);
+        double s = pf / ptot;
+        pb *= s; pperp *= s; ptot = pf; gam_pf = gam_f;
+    }
+}
+
+// prob_return.jl:217-344.  Runs as a nested loop on the lane: retro passes are ~1e-3 of all passes.
+template <bool DEBUG>
+__device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd, double prp_x, double& ptot,
+                                        double& pb, double& pperp, double& gam_pf, double& acct, double weight,
+                                        int& tcut_curr, double& phi_out, long long& n_steps) {
+    const int ng = P.n_grid;
+    const bool custom = P.flags & F_CUSTOM_EPSB;
+    const double xn_per = 10.0, phi_step = TWO_PI / xn_per;
+    const double t_step_fac = TWO_PI * P.aa * P.mp * P.c * gd / xn_per;
+    const double ux = -P.ux[ng], gsf = P.gsf[ng], gef = P.gef[ng];
+    double B = P.bt[ng];
+    if (custom) B *= sqrt(P.x_grid_stop / prp_x);
+    const double bcos = P.costh[ng], bsin = P.sinth[ng];
+    const double Bcmb = P.B_CMBz * gef;
+    double B2 = B * B + Bcmb * Bcmb;
+    bool lose = false;
+    double x = prp_x;
+    double phi = uniform<DEBUG>(rng, P) * TWO_PI;
+    long long steps = 0;
+    for (;;) {
+        steps++;
+        double x_old = x, phi_old = phi, ptot_old = ptot;
+        double cos_old = pb / ptot, sin_old = pperp / ptot;
+        if (custom) {
+            B = P.bt[ng] * sqrt(P.x_grid_stop / x);
+            B2 = B * B + Bcmb * Bcmb;
+            gd = 1 / (P.zz * B);
+        }
+        double gyro_rad = pperp * P.c * gd;
+        phi = mod2pi(phi_old + phi_step);
+        double t_step = t_step_fac * gam_pf;
+        double x_move = pb * t_step_fac / (P.aa * P.mp);
+        double gyr = bsin != 0.0 ? gyro_rad * bsin * (cos(phi) - cos(phi_old)) : 0.0;
+        x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
+        acct += t_step * gef;
+        if ((P.flags & F_TCUTS) && tcut_curr <= P.n_tcuts && acct >= P.tcuts[tcut_curr - 1]) {
+            tcut_track(P, tcut_curr, weight, ptot);
+            tcut_curr++;
+        }
+        phi = TWO_PI * uniform<DEBUG>(rng, P);
+        pb = (2 * uniform<DEBUG>(rng, P) - 1) * ptot;
+        pperp = sqrt_guard(P, ptot * ptot - pb * pb);
+        if ((P.flags & F_RAD_LOSSES) && P.aa < 1) ptot = radiation_loss(P, B2, ptot, t_step);
+        if (ptot <= 0) {
+            ptot = 1.0e-99; gam_pf = 1.0; lose = true;
+            break;
+        }
+        if (P.flags & F_KEEP_NEW_PITCH) {
+            double r = ptot / ptot_old;
+            pb *= r; pperp *= r;
+        } else {
+            pb = ptot * cos_old; pperp = ptot * sin_old;
+        }
+        gam_pf = hypot(1.0, ptot / P.mc);
+        if (x < prp_x) break;
+        if (steps >= P.retro_cap) { count(P, CNT_RETRO_CAP); break; }
+    }
+    phi_out = phi;
+    n_steps += steps;
+    return lose;
+}
+
+// particle_finish.jl:46-107 with the zone values the loop last loaded (particle_loop.jl:503-507)
+__device__ __noinline__ void particle_finish(const DevParams& P, int reason, double pb, double pperp, double gam_pf,
+                                             double phi, double ux, double gsf, double bcos, double bsin,
+                                             double weight) {
+    double E0 = P.m * (P.c * P.c);
+    double ptot_sk, sx, sz, gam_sk;
+    transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
+    int ip = min(psd_bin_momentum(P, ptot_sk), MCS_PSD_MAX), jt = min(psd_bin_angle(P, sx, ptot_sk), MCS_PSD_MAX);
+    double wf;
+    if (ptot_sk > fabs(SPIKE_AWAY * sx)) wf = gam_sk * P.m * SPIKE_AWAY / ptot_sk;
+    else wf = gam_sk * (P.m / fabs(sx));
+    if (reason == 1) {
+        atomicAdd(&P.t.esc_dn[ip + E1 * jt], weight * wf);
+    } else if (reason == 2) {
+        atomicAdd(&P.t.scalars[SC_ESC_FLUX], weight);
+        atomicAdd(&P.t.esc_up[ip + E1 * jt], weight * wf);
+        bool rel = (gam_sk - 1) >= P.E_rel_pt;  // F-8
+        double Ek = rel ? (gam_sk - 1) * E0 : ptot_sk * ptot_sk / (2 * P.m);
+        double en_add = Ek * weight;
+        atomicAdd(&P.t.scalars[SC_PX_ESC_FEB], fabs(sx) * weight);
+        atomicAdd(&P.t.scalars[SC_EN_ESC_FEB], en_add);
+        atomicAdd(&P.t.esc_en_eff[ip], en_add);
+        atomicAdd(&P.t.esc_num_eff[ip], weight);
+    }
+}
+
+// all_flux.jl:86-158 once the zone has changed (or an x_spec / FEB detector may have been crossed).
+// sh_flux: per-block shared tallies [pxx | pxz | efl | crossings] of n_grid entries each.
+__device__ __noinline__ void flux_tallies(const DevParams& P, double* sh_flux, double pb, double pperp, double ptot,
+                                          double gam_pf, double phi, double weight, int i_grid, int i_grid_old,
+                                          double ux, double gsf, double bcos, double bsin, double x, double x_old,
+                                          bool inj) {
+    const int ng = P.n_grid;
+    double ptot_sk, sx, sz, gam_sk;
+    transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
+    double pt_o_px_sk, abs_inv_vx;
+    if (ptot_sk > fabs(sx * SPIKE_AWAY)) {
+        pt_o_px_sk = SPIKE_AWAY;
+        abs_inv_vx = fabs(SPIKE_AWAY / ux);
+    } else {
+        pt_o_px_sk = ptot_sk / sx;
+        abs_inv_vx = fabs(gam_sk * P.aa * P.mp / sx);
+    }
+    double en_add;
+    if ((gam_sk - 1) > P.E_rel_pt) en_add = (gam_sk - 1) * P.m * (P.c * P.c) * weight;
+    else en_add = ptot_sk * ptot_sk / (2 * P.m) * weight;
+
+    if (P.n_xspec > 0) {  // calculate_x_spec_spectra! :164-190
+        double pt_o_px_pf = fmin(fabs(ptot / pb), SPIKE_AWAY);
+        int ipt = psd_bin_momentum(P, ptot_sk), ipf = psd_bin_momentum(P, ptot);
+        for (int i = 0; i < P.n_xspec; i++) {
+            double xs = P.x_spec[i];
+            if ((x_old < xs && x >= xs) || (x <= xs && x_old > xs)) {
+                atomicAdd(&P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
+                double F = fabs(pb / sx) * (gam_sk / gam_pf);
+                atomicAdd(&P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
+            }
+        }
+    }
+    int lo, hi;
+    bool up = !(x > x_old);
+    double sign_fac = up ? -1.0 : 1.0;
+    if (!up) { lo = i_grid_old + 1; hi = i_grid; }
+    else { lo = i_grid + 1; hi = i_grid_old; if (inj) lo = max(lo, P.i_grid_feb + 1); }  // :223-225
+    if (lo <= hi) {
+        const double f_pxx = sign_fac * sx * weight * P.gam0 * P.u0;
+        const double f_pxz = fabs(sz) * weight * P.gam0 * P.u0;
+        const double f_en = sign_fac * en_add * P.gam0 * P.u0;
+        if (inj) {
+            int ipt = psd_bin_momentum(P, ptot_sk), jth = psd_bin_angle(P, sx, ptot_sk);
+            const size_t stride = (size_t)(P.M + 2) * (size_t)(P.T + 2);
+            double* cell = P.t.psd + (size_t)ipt + (size_t)(P.M + 2) * (size_t)jth + stride * (size_t)(lo - 1);
+            const double w = weight * abs_inv_vx;
+            for (int i = lo; i <= hi; i++, cell += stride) {
+                atomicAdd(&sh_flux[i - 1], f_pxx);
+                atomicAdd(&sh_flux[ng + i - 1], f_pxz);
+                atomicAdd(&sh_flux[2 * ng + i - 1], f_en);
+                atomicAdd(cell, w);
+            }
+        } else {
+            // thermal particle: one log record per boundary (all_flux.jl:242-254); slots claimed in one atomic
+            const int nrec = hi - lo + 1;
+            long long base = (long long)atomicAdd(&P.t.counters[CNT_LOG], (unsigned long long)nrec);
+            const double w = weight * abs_inv_vx;
+            long long over = 0;
+            for (int k = 0; k < nrec; k++) {
+                int i = up ? hi - k : lo + k;  // reference order: downstream ascending, upstream descending
+                atomicAdd(&sh_flux[i - 1], f_pxx);
+                atomicAdd(&sh_flux[ng + i - 1], f_pxz);
+                atomicAdd(&sh_flux[2 * ng + i - 1], f_en);
+                atomicAdd((unsigned long long*)&sh_flux[3 * ng + i - 1], 1ull);
+                long long slot = base + k;
+                if (slot < P.t.na_cr) {
+                    P.t.tg[slot] = i; P.t.tpx[slot] = sx; P.t.tpt[slot] = ptot_sk; P.t.tw[slot] = w;
+                } else {
+                    over++;
+                }
+            }
+            if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
+        }
+    }
+    if (inj && x < P.feb_up && x_old >= P.feb_up) {  // :155-158
+        atomicAdd(&P.t.scalars[SC_EN_ESC_UP], en_add * P.gam0 * P.u0);
+        atomicAdd(&P.t.scalars[SC_PX_ESC_UP], -(sx * weight * P.gam0 * P.u0));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The transport kernel.
+template <bool DEBUG>
+__global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant__ DevParams P) {
+    extern __shared__ double sh_flux[];  // [4*n_grid]
+    const int ng = P.n_grid;
+    for (int i = threadIdx.x; i < 4 * ng; i += blockDim.x) sh_flux[i] = 0.0;
+    __syncthreads();
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t flags = P.flags;
+    const bool custom = flags & F_CUSTOM_EPSB, dont_scatter = flags & F_DONT_SCATTER;
+
+    // lane state -------------------------------------------------------------------------------
+    long long ip = -1;
+    bool queue_empty = false;
+    double weight = 0, ptot = 0, pb = 0, pperp = 0, x = 0, x_old = 0, xn_per = 0, prp_x = 0, acct = 0, phi = 0;
+    double gam_pf = 1, gd = 0, grt = 0, gr = 0, gper = 0, t_step = 0;
+    double ux = 0, gsf = 1, gef = 1, bsin = 0, bcos = 1;
+    int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1;
+    bool down = false, inj = false;
+    long long retro_steps = 0;
+    unsigned long long tot_helix = 0, tot_retro = 0;
+    Rng rng;
+    rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
+    int slot = -1;
+
+    for (;;) {
+        // ---- refill idle lanes from the global queue: one atomic per warp ------------------------
+        unsigned need = __ballot_sync(FULL, ip < 0 && !queue_empty);
+        if (need) {
+            long long base = 0;
+            int leader = __ffs(need) - 1;
+            if (lane == leader) base = (long long)atomicAdd(&P.t.counters[CNT_QUEUE], (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (ip < 0 && !queue_empty) {
+                long long mine = base + __popc(need & ((1u << lane) - 1u));
+                if (mine < P.n_use) {
+                    ip = mine;
+                    // particle_loop.jl:44-96, 131-153
+                    weight = P.cur.weight[ip]; ptot = P.cur.ptot[ip]; pb = P.cur.pb[ip]; x = P.cur.x[ip];
+                    xn_per = P.cur.xn_per[ip]; prp_x = P.cur.prp_x[ip]; acct = P.cur.acctime[ip]; phi = P.cur.phi[ip];
+                    i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
+                    down = P.cur.down[ip]; inj = P.cur.inj[ip];
+                    helix = 0; i_return = -1; t_step = 0.0; x_old = 0.0; retro_steps = 0;
+                    gam_pf = hypot(1.0, ptot / P.mc);
+                    gd = 1 / (P.zz * P.bt[i_grid]);
+                    if (custom && x > P.x_grid_stop) gd *= sqrt(x / P.x_grid_stop);
+                    grt = ptot * P.c * gd;
+                    gper = TWO_PI * gam_pf * P.m * P.c * gd;
+                    iz = i_grid;
+                    ux = P.ux[iz]; gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                    pperp = perpendicular_momentum(P, ptot, pb);
+                    gr = pperp * P.c * gd;
+                    rng.n = 0; rng.c1 = (uint32_t)(P.first_global + ip); rng.exhausted = false;
+                    if (DEBUG) {
+                        rng.ru = nullptr; rng.rn = 0;
+                        if (P.replay_u != nullptr && ip < P.replay_n) {
+                            rng.ru = P.replay_u + P.replay_off[ip];
+                            rng.rn = P.replay_off[ip + 1] - P.replay_off[ip];
+                        }
+                        slot = P.trace_slot ? P.trace_slot[ip] : -1;
+                    }
+                } else {
+                    queue_empty = true;
+                }
+            }
+        }
+        if (__all_sync(FULL, ip < 0)) break;
+
+        if (ip >= 0) {
+            // ---- one pass of the helix loop (particle_loop.jl:154-499) -----------------------------
+            int fin = -1;  // -1 running; 0 saved; 1..4 i_reason; 5 error
+            helix++;
+            if (helix > P.helix_cap) {
+                fin = 1;  // K-1
+            } else {
+                if (i_return == 1) {
+                    pperp = perpendicular_momentum(P, ptot, pb);
+                    gr = pperp * P.c * gd;
+                } else {
+                    // Code Block 3
+                    const int iz_old = iz;
+                    if (i_grid != iz) {
+                        iz = i_grid;
+                        ux = P.ux[iz]; gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                    }
+                    double bmag = (custom && x > P.x_grid_stop) ? P.bt[ng] * sqrt(P.x_grid_stop / x) : P.bt[iz];
+                    gd = 1 / (P.zz * bmag);
+                    if (iz != iz_old && ux != P.ux[iz_old]) {
+                        transform_p_PSP(P, iz_old, iz, ptot, pb, pperp, gam_pf, phi);
+                        gr = pperp * P.c * gd;
+                        grt = ptot * P.c * gd;
+                    }
+                    if (P.energy_transfer_frac > 0 && !inj && x_old <= 0 && i_grid_old != i_grid)
+                        do_energy_transfer(P, i_grid, i_grid_old, ptot, pb, pperp, gam_pf, weight);
+                    if (dont_scatter && x > 10 * gr) {
+                        i_return = 0; fin = 1;
+                    } else if (ptot > P.pmax_cutoff) {
+                        double ptot_sk, sx, sz, gam_sk;
+                        transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
+                        if (ptot_sk > P.pmax_cutoff) fin = 2;
+                    }
+                    if (fin < 0 && inj && x < P.feb_up) fin = 2;
+                    if (fin < 0 && P.age_max > 0 && acct > P.age_max) fin = 3;
+                    if (fin < 0 && (flags & F_RAD_LOSSES) && P.aa < 1) {
+                        double p_old = ptot, Bcmb = P.B_CMBz * gef;
+                        ptot = radiation_loss(P, bmag * bmag + Bcmb * Bcmb, ptot, t_step);
+                        if (ptot <= 0) {
+                            ptot = 1.0e-99; pb = 1.0e-99; pperp = 1.0e-99; gam_pf = 1;
+                            fin = 4;
+                        } else {
+                            gam_pf = hypot(ptot / P.mc, 1.0);
+                            pb *= ptot / p_old;
+                            pperp *= ptot / p_old;
+                            grt = ptot * P.c * gd;
+                            gr = pperp * P.c * gd;
+                        }
+                    }
+                    if (fin < 0) {
+                        if (!dont_scatter) {
+                            // scattering.jl:29-101
+                            double grt_s;
+                            if (P.aa < 1 && ptot < P.pe_crit) {
+                                grt_s = P.pe_crit * P.c * gd;
+                                gper = TWO_PI * P.gam_e_crit * P.mc * gd;
+                            } else {
+                                grt_s = ptot * P.c * gd;
+                                gper = TWO_PI * gam_pf * P.mc * gd;
+                            }
+                            double vp_tg = TWO_PI * grt_s, lambda = P.eta_mfp * grt_s;
+                            double cos_max = cos(sqrt(6 * vp_tg / (xn_per * lambda)));
+                            double cos_old = pb / ptot, sin_old = pperp / ptot;
+                            double cos_d = 1 - uniform<DEBUG>(rng, P) * (1 - cos_max);
+                            double sin_d = sqrt_guard(P, 1 - cos_d * cos_d);
+                            double phi_s = uniform<DEBUG>(rng, P) * TWO_PI - PI;
+                            double sps, cps;
+                            sincos(phi_s, &sps, &cps);
+                            double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
+                            double sin_new = sqrt_guard(P, 1 - cos_new * cos_new);
+                            pb = ptot * cos_new;
+                            pperp = ptot * sin_new;
+                            double phi_p = phi + HALF_PI;
+                            if (sin_new != 0) {
+                                double s = sps * sin_d / sin_new;
+                                if (fabs(s) > SIN_UPPER_LIMIT) s = copysign(SIN_UPPER_LIMIT, s);
+                                phi_p += asin(s);
+                            }
+                            phi = phi_p - HALF_PI;
+                        }
+                        if (down) {
+                            acct += t_step * gef;
+                            if ((flags & F_TCUTS) && tcut <= P.n_tcuts && acct >= P.tcuts[tcut - 1]) {
+                                tcut_track(P, tcut, weight, ptot);
+                                tcut++;
+                            }
+                            if (ptot > P.pcut) fin = 0;  // saved below
+                        }
+                        if (fin < 0) xn_per = x > grt ? P.xn_coarse : P.xn_fine;
+                    }
+                }
+                if (fin < 0) {
+                    // Code Block 2
+                    x_old = x;
+                    const double phi_old = phi;
+                    t_step = gper / xn_per;
+                    bool err = false;
+                    for (int pass = 0;; pass++) {  // no_DSA_loop :510-571
+                        phi = mod2pi(phi + TWO_PI / xn_per);
+                        double x_move = pb * t_step / (gam_pf * P.m);
+                        double gyr = bsin != 0.0 ? gr * bsin * (cos(phi) - cos(phi_old)) : 0.0;
+                        x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
+                        if (x <= 0 && x_old > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)) {
+                            if ((flags & F_DONT_DSA) || uniform<DEBUG>(rng, P) > P.inj_frac) {
+                                if (pb < 0) pb = -pb; else phi = uniform<DEBUG>(rng, P) * TWO_PI;
+                            } else break;
+                        } else break;
+                        if (pass > 1000) { err = true; break; }
+                    }
+                    if (x_old < 0 && x >= 0) {
+                        down = true;
+                        double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
+                        prp_x = fmax(prp_x, L);
+                    }
+                    if (down && x < 0) inj = true;
+
+                    // all_flux.jl:65-82: linear scans from the current zone (K-3)
+                    i_grid_old = i_grid;
+                    if (x > x_old) {
+                        int k = i_grid + 1;
+                        while (k <= ng + 1 && !(P.xg[k] > x)) k++;
+                        if (k > ng + 1) err = true;
+                        i_grid = k - 1;
+                    } else {
+                        int k = i_grid;
+                        while (k >= 0 && !(P.xg[k] <= x)) k--;
+                        if (k < 0) err = true;
+                        i_grid = k;
+                    }
+                    if (err) {
+                        fin = MCS_FATE_ERROR;
+                        i_grid = i_grid_old;
+                    } else {
+                        if (!(i_grid == i_grid_old && i_grid > P.i_grid_feb && P.n_xspec == 0))
+                            flux_tallies(P, sh_flux, pb, pperp, ptot, gam_pf, phi, weight, i_grid, i_grid_old, ux, gsf,
+                                         bcos, bsin, x, x_old, inj);
+                        // downstream_test :595-637
+                        bool do_prob_ret = true, went_retro = false, lose_pt = false;
+                        if (P.feb_dn > 0 && x > P.feb_dn) {
+                            i_return = 0; do_prob_ret = false;
+                        } else if (x > 1.1 * prp_x) {
+                            double v_fac;
+                            if (P.aa < 1 && ptot < P.pe_crit) {
+                                double gyro_fac = P.pe_crit * P.c * gd;
+                                v_fac = gyro_fac * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
+                            } else {
+                                v_fac = grt * ptot / (P.m * gam_pf * P.u2);
+                            }
+                            double L = P.eta_mfp / 3 * v_fac;
+                            if (x > 6.91 * L) { i_return = 0; do_prob_ret = false; }
+                        }
+                        if (do_prob_ret) {
+                            // prob_return.jl:36-173
+                            i_return = 2;
+                            if (x < P.x_grid_stop) {
+                            } else if (x_old < P.x_grid_stop && P.x_grid_stop <= x) {
+                                double gyro_tmp = (custom && x > P.x_grid_stop) ? sqrt(P.x_grid_stop / x) : 1.0;
+                                double g2 = ptot * P.c * gyro_tmp / (P.qcgs * P.bmag2);  // K-5
+                                double L = P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2);
+                                prp_x = x + 3 * L;
+                            } else if (x_old < prp_x && x >= prp_x) {
+                                double vt = ptot / (gam_pf * P.aa * P.mp);
+                                double r = (vt - P.u2) / (vt + P.u2);
+                                if (vt < P.u2 || uniform<DEBUG>(rng, P) > r * r) {
+                                    i_return = 0;
+                                } else {
+                                    i_return = 1;
+                                    if (!(flags & F_RETRO)) {
+                                        fin = MCS_FATE_ERROR;  // reference: error() prob_return.jl:134
+                                    } else {
+                                        went_retro = true;
+                                        lose_pt = retro_time<DEBUG>(P, rng, gd, prp_x, ptot, pb, pperp, gam_pf, acct,
+                                                                    weight, tcut, phi, retro_steps);
+                                        if (lose_pt) i_return = 0;
+                                        x = prp_x;
+                                    }
+                                }
+                            } else if (P.aa < 1 && ptot < P.pcut_prev && helix % 1000 == 0) {
+                                double g2 = ptot * P.c * gd;
+                                double L = P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2);
+                                if (x > 2.0e3 * L) prp_x = 0.8 * x;
+                                else prp_x = fmin(prp_x, P.x_grid_stop + L * pow(P.pcut_prev / ptot, 5.0));
+                            }
+                        }
+                        if (DEBUG && slot >= 0) {
+                            int k = P.trace_cnt[slot];
+                            if (k < P.trace_max) {
+                                McsTraceRec& r = P.trace_recs[(size_t)slot * P.trace_max + k];
+                                r.x_cm = x; r.ptot_pf = ptot; r.pb_pf = pb; r.phi_rad = phi; r.acctime_sec = acct;
+                                r.prp_x_cm = prp_x; r.i_grid = i_grid; r.helix_count = helix;
+                                r.flags = (down ? 1 : 0) | (inj ? 2 : 0) | (went_retro ? 4 : 0) | ((i_return + 1) << 8);
+                                r.n_draws = (int)rng.n;
+                                P.trace_cnt[slot] = k + 1;
+                            }
+                        }
+                        if (fin < 0 && i_return == 0) {
+                            double vel = ptot / P.m;
+                            if ((gam_pf - 1) >= P.E_rel_pt) vel /= gam_pf;
+                            atomicAdd(&P.t.scalars[SC_SUMP], ptot / 3 * vel * weight * P.n0);
+                            atomicAdd(&P.t.scalars[SC_SUMKE], (gam_pf - 1) * P.m * (P.c * P.c) * weight * P.n0);
+                            fin = lose_pt ? 4 : 1;
+                        }
+                        if (DEBUG && fin < 0 && rng.exhausted) fin = MCS_FATE_ERROR;
+                    }
+                }
+            }
+            // ---- the particle left the loop --------------------------------------------------------
+            if (fin >= 0) {
+                if (DEBUG && rng.exhausted) fin = MCS_FATE_ERROR;
+                if (fin == 0) {  // particle_loop.jl:361-380
+                    P.l_save[ip] = 1;
+                    P.saved.weight[ip] = weight; P.saved.ptot[ip] = ptot; P.saved.pb[ip] = pb; P.saved.x[ip] = x;
+                    P.saved.grid[ip] = i_grid; P.saved.down[ip] = down; P.saved.inj[ip] = inj;
+                    P.saved.xn_per[ip] = xn_per; P.saved.prp_x[ip] = x < prp_x ? prp_x : x * 1.1;
+                    P.saved.acctime[ip] = acct; P.saved.phi[ip] = phi; P.saved.tcut[ip] = tcut;
+                } else if (fin <= 4) {
+                    particle_finish(P, fin, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, weight);
+                } else {
+                    count(P, CNT_ERR);
+                }
+                P.fate[ip] = fin; P.helix[ip] = helix; P.retro[ip] = retro_steps; P.draws[ip] = rng.n;
+                count(P, CNT_FATE0 + fin);
+                tot_helix += (unsigned long long)helix;
+                tot_retro += (unsigned long long)retro_steps;
+                ip = -1;
+            }
+        }
+    }
+
+    // ---- warp totals, block partials ----------------------------------------------------------------
+    unsigned long long n_saved_dummy = 0;
+    (void)n_saved_dummy;
+    for (int o = 16; o > 0; o >>= 1) {
+        tot_helix += __shfl_xor_sync(FULL, tot_helix, o);
+        tot_retro += __shfl_xor_sync(FULL, tot_retro, o);
+    }
+    if (lane == 0) {
+        if (tot_helix) atomicAdd(&P.t.counters[CNT_HELIX], tot_helix);
+        if (tot_retro) atomicAdd(&P.t.counters[CNT_RETRO], tot_retro);
+    }
+    __syncthreads();
+    double* part = P.t.block_partials + (size_t)blockIdx.x * (size_t)(4 * ng);
+    for (int i = threadIdx.x; i < 4 * ng; i += blockDim.x) part[i] = sh_flux[i];
+}
+
+// Sum the per-block partials in block order (run-to-run deterministic across blocks) into the ion totals.
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int ng, double* pxx,
+                                       double* pxz, double* efl, unsigned long long* ncross) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * ng) return;
+    if (i < 3 * ng) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * (4 * ng) + i];
+        double* dst = i < ng ? pxx + i : (i < 2 * ng ? pxz + (i - ng) : efl + (i - 2 * ng));
+        *dst += s;
+    } else {
+        unsigned long long s = 0;
+        const unsigned long long* pu = reinterpret_cast<const unsigned long long*>(partials);
+        for (int b = 0; b < n_blocks; b++) s += pu[(size_t)b * (4 * ng) + i];
+        ncross[i - 3 * ng] += s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// new_pcut (cuts.jl:34-98) on device: order-preserving compaction of l_save, then i_mult clones each.
+__global__ void count_saved_kernel(const uint8_t* __restrict__ l_save, long long n, int* block_counts) {
+    __shared__ int sh[32];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int v = (i < n && l_save[i]) ? 1 : 0;
+    unsigned b = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) block_counts[blockIdx.x] = s;
+    }
+}
+
+// single block: exclusive scan of block_counts (n_blocks entries) into block_offsets; total -> *total
+__global__ void scan_blocks_kernel(const int* __restrict__ counts, int n_blocks, long long* offsets, long long* total) {
+    __shared__ long long sh[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        long long v = i < n_blocks ? counts[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < blockDim.x; o <<= 1) {
+            long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n_blocks) offsets[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[blockDim.x - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void compact_saved_kernel(const uint8_t* __restrict__ l_save, long long n, const long long* __restrict__ offsets,
+                                     long long* saved_idx) {
+    __shared__ int sh[32];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int v = (i < n && l_save[i]) ? 1 : 0;
+    unsigned b = __ballot_sync(0xffffffffu, v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int k = 0; k < w; k++) before += sh[k];
+    if (v) saved_idx[offsets[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u))] = i;
+}
+
+__global__ void clone_kernel(PopPtrs src, PopPtrs dst, const long long* __restrict__ saved_idx, long long n_out,
+                             long long i_mult) {
+    long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    long long j = saved_idx[o / i_mult];
+    dst.weight[o] = src.weight[j] / (double)i_mult;  // cuts.jl:77
+    dst.ptot[o] = src.ptot[j]; dst.pb[o] = src.pb[j]; dst.x[o] = src.x[j]; dst.grid[o] = src.grid[j];
+    dst.down[o] = src.down[j]; dst.inj[o] = src.inj[j]; dst.xn_per[o] = src.xn_per[j]; dst.prp_x[o] = src.prp_x[j];
+    dst.acctime[o] = src.acctime[j]; dst.phi[o] = src.phi[j]; dst.tcut[o] = src.tcut[j];
+}
+
+__global__ void fill_defaults_kernel(PopPtrs p, long long n, int has_down, int has_inj, int has_xn, int has_prp,
+                                     int has_acc, int has_tcut, double xn_fine, double x_grid_stop) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!has_down) p.down[i] = 0;
+    if (!has_inj) p.inj[i] = 0;
+    if (!has_xn) p.xn_per[i] = xn_fine;
+    if (!has_prp) p.prp_x[i] = x_grid_stop;
+    if (!has_acc) p.acctime[i] = 0.0;
+    if (!has_tcut) p.tcut[i] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Roofline denominators measured in place (MEASURED_PEAKS.json has no FP64 entry).
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void atomic_peak_kernel(double* cells, long long n_cells, int iters) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < iters; i++) {
+        s = s * 1664525u + 1013904223u;
+        long long idx = (long long)(((unsigned long long)s * (unsigned long long)n_cells) >> 32);
+        atomicAdd(&cells[idx], 1.0);
+    }
+}
+
+}  // namespace mcs

@@ -676,3 +676,33 @@ def init_pop(run: Run, prof: Profile, i_ion: int, rng: np.random.Generator) -> I
     phi = 2 * math.pi * rng.random(n)
     pop = dict(weight=w, ptot_pf=ptot, pb_pf=pb, x_cm=x, grid=grid, phi_rad=phi)
     return InitPop(pop=pop, pxx_flux=pxx, pxz_flux=pxz, energy_flux=efl, weight_running=float(w[0]) if n else 0.0)
+
+
+def synthetic_precursor(run: Run, r_sub: float = 3.0, scale_rg: float = 5.0) -> Profile:
+    """A smoothed (nonlinear-shock-shaped) profile for the "nonlinear" config without running smoothers.jl.
+
+    smooth_grid_par (smoothers.jl:54-349) stays in host Julia and is out of scope; what the transport loop sees
+    of it is a velocity profile that decreases monotonically through a precursor to a weak subshock, with the
+    derived arrays recomputed exactly as smoothers.jl:324-346 does.  Here u(x) = u_sub + (u0 - u_sub)(1 - e^{x/L})
+    for x < 0 (L = scale_rg rg0) with a subshock of compression r_sub, and u = u0/r_comp downstream, so that the
+    total compression is the run's r_comp and every upstream zone has its own flow speed (one transform_p_PSP
+    per zone change)."""
+    p = run.profile
+    n = len(p.x_grid_rg)
+    u_dn = run.u0 / run.r_comp
+    u_sub = min(u_dn * r_sub, run.u0)
+    ux = np.where(p.x_grid_rg < 0, u_sub + (run.u0 - u_sub) * (1 - np.exp(np.minimum(p.x_grid_rg, 0.0) / scale_rg)), u_dn)
+    ux[0] = run.u0
+    gsf = 1 / np.sqrt(1 - (ux / CL) ** 2)
+    bef = (run.u0 - ux) / (CL - run.u0 * ux / CL)
+    gef = 1 / np.sqrt(1 - bef**2)
+    z = (run.gam0 * run.u0) / (gsf * ux)
+    comp = 1 + (np.sqrt(1 / 3 + 2 / 3 * z**2) - 1) * run.inp.b_field_turbulence
+    bt = run.bmag0 * (1 + (comp - 1) * run.inp.b_field_amplify)
+    if run.inp.use_custom_epsB:
+        n0 = sum(s.n0 * s.mass for s in run.species) / MP
+        e0 = n0 * MP * CL**2
+        ed = (run.F_energy_upstream + run.gam0 * run.u0 * e0) / ux - run.F_px_upstream
+        bt = np.sqrt(np.abs(8 * math.pi * p.epsB * ed))
+    return Profile(x_grid_rg=p.x_grid_rg.copy(), x_grid_cm=p.x_grid_cm.copy(), ux_sk=ux, uz_sk=np.zeros(n), utot=ux.copy(),
+                   gam_sf=gsf, gam_ef=gef, beta_ef=bef, btot=bt, theta=p.theta.copy(), epsB=p.epsB.copy())

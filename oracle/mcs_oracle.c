@@ -1090,3 +1090,34 @@ int mcs_measure_atomic_peak(McsHandle* h, int64_t n, double* g) {
     (void)h; (void)n; (void)g;
     return fail(MCS_ERR_UNSUPPORTED, "cpu oracle");
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Test-only hooks (not part of include/mcs.h): let the known-answer tests call the restated    */
+/* reference functions one at a time.                                                           */
+MCS_API void mcso_transform_p_PS(McsHandle* h, double aa, double pb, double pperp, double gam_pf, double phi, double ux,
+                                 double gsf, double bcos, double bsin, double out[5]) {
+    double psk[3];
+    transform_p_PS(h, aa, pb, pperp, gam_pf, phi, ux, 0.0, ux, gsf, bcos, bsin, &out[0], psk, &out[4]);
+    out[1] = psk[0]; out[2] = psk[1]; out[3] = psk[2];
+}
+MCS_API void mcso_transform_p_PSP(McsHandle* h, double aa, double io[5] /* ptot pb pperp gam phi */, const double old6[6],
+                                  const double new6[6] /* ux uz ut gsf bcos bsin */) {
+    transform_p_PSP(h, aa, &io[1], &io[2], &io[3], &io[4], old6[0], old6[1], old6[2], old6[3], old6[4], old6[5], new6[0],
+                    new6[1], new6[2], new6[3], new6[4], new6[5], &io[0]);
+}
+MCS_API void mcso_scattering(McsHandle* h, uint32_t stream, int n_kicks, double aa, double gyro_denom, double ptot,
+                             double gam_pf, double xn_per, double io[4] /* gyro_period pb pperp phi */) {
+    Rng rng; memset(&rng, 0, sizeof rng);
+    rng.key[0] = (uint32_t)h->cfg.seed; rng.key[1] = (uint32_t)(h->cfg.seed >> 32); rng.ctr[1] = stream;
+    for (int k = 0; k < n_kicks; k++) scattering(h, &rng, aa, gyro_denom, ptot, gam_pf, xn_per, &io[0], &io[1], &io[2], &io[3]);
+}
+MCS_API int mcso_psd_bin_momentum(McsHandle* h, double p) { return get_psd_bin_momentum(h, p); }
+MCS_API int mcso_psd_bin_angle(McsHandle* h, double px, double p) { return get_psd_bin_angle(h, px, p); }
+MCS_API double mcso_radiation_loss(McsHandle* h, double B2, double p, double dt) { return radiation_loss(h, B2, p, dt); }
+MCS_API double mcso_mod2pi(double x) { return mod2pi(x); }
+MCS_API void mcso_philox(uint64_t seed, uint32_t c1, uint32_t c2, uint32_t c3, int n, double* out) {
+    Rng rng; memset(&rng, 0, sizeof rng);
+    rng.key[0] = (uint32_t)seed; rng.key[1] = (uint32_t)(seed >> 32); rng.ctr[1] = c1; rng.ctr[2] = c2; rng.ctr[3] = c3;
+    for (int i = 0; i < n; i++) out[i] = rng_uniform(&rng);
+}
+MCS_API void mcso_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }

@@ -1,0 +1,46 @@
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py FROM THE ORACLE — the
+reference has none) against the oracle (CPU) and the CUDA kernel (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from golden.make_golden import CASES, run_case
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INT_KEYS = ("_n", "_fate", "_helix_count", "_retro_steps", "_n_draws", "_l_save", "_grid", "_tcut", "_downstream", "_inj",
+            "_idx", "num_crossings", "t_stats", "t_log_grid")
+
+
+def check(got, name, ftol):
+    want = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    assert sorted(got) == sorted(want.files)
+    for k in want.files:
+        a, b = want[k], got[k]
+        assert a.shape == b.shape, k
+        if k.endswith(INT_KEYS):
+            assert np.array_equal(a, b), f"{name}:{k} integer data differs"
+        else:
+            s = np.maximum(np.abs(a), np.abs(b))
+            s = np.where(s > 0, s, 1.0)
+            if "saved_pb_pf" in k:
+                s = np.maximum(s, np.abs(want[k.replace("pb_pf", "ptot_pf")]))
+            if "saved_phi_rad" in k:
+                s = np.maximum(s, 2 * np.pi)
+            if "saved_x_cm" in k or "saved_prp_x_cm" in k:
+                s = np.maximum(s, np.abs(want[k.replace("prp_x_cm", "x_cm")]).max() * 1e-3)
+            err = float((np.abs(a - b) / s).max()) if a.size else 0.0
+            assert err <= ftol, f"{name}:{k} differs by {err:.3e}"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_golden(olib, name):
+    mk, ion = CASES[name]
+    check(run_case(olib, mk(), ion), name, ftol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_reproduces_golden(clib, name):
+    mk, ion = CASES[name]
+    check(run_case(clib, mk(), ion), name, ftol=1e-9)

@@ -1,0 +1,258 @@
+"""Parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): integer decisions — zone, pcut/save, escape reason, pass counts, number of
+uniforms drawn, crossing counts — bit-exact; continuous state within 1e-12 relative in replay mode, measured on
+each quantity's natural scale (helpers.natural_scales).  After thousands of chaotic scattering steps the two
+libms (CUDA vs glibc: <= 2 ulp apart per call) have random-walked apart, so end-of-pcut state is held to 1e-9.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (LADDER, compare_saved, make_engine, natural_scales, rel_close, small_inputs, sorted_log,
+                     start_ion)
+from mcs_b200 import abi, driver, problem
+
+pytestmark = pytest.mark.gpu
+
+TOL_END_STATE = 1e-9
+TOL_REPLAY = 1e-12
+TOL_TALLY = 1e-9
+
+
+def _ion_for(name, run):
+    return 3 if name == "multi" else 1
+
+
+@pytest.mark.parametrize("name", ["bundled", "planar", "relativistic", "nonlinear", "multi"])
+def test_per_particle_parity(olib, clib, name):
+    inp = small_inputs()[name]
+    run = problem.setup_run(inp)
+    prof = problem.synthetic_precursor(run) if name == "nonlinear" else run.profile
+    ions = [1, 2, 3] if name == "multi" else [1]
+    pool = np.zeros(run.n_grid)
+    for i_ion in ions:
+        sp = run.species[i_ion - 1]
+        eo, ec = make_engine(olib, run), make_engine(clib, run)
+        for e in (eo, ec):
+            start_ion(e, run, i_ion=i_ion, prof=prof, pool=pool.copy())
+        p_hi = problem.pcut_hi(inp.en_pcut_hi, sp.mass)
+        worst = {}
+        for k, pcut in enumerate(run.pcuts, start=1):
+            n = eo.population_size()
+            assert ec.population_size() == n
+            prev = run.pcuts[k - 2] if k > 1 else 0.0
+            (ns_o, st_o), (ns_c, st_c) = eo.run_pcut(k, pcut, prev), ec.run_pcut(k, pcut, prev)
+            fo, fc = eo.get_fates(n), ec.get_fates(n)
+            for key in ("fate", "helix_count", "retro_steps", "n_draws"):
+                assert np.array_equal(fo[key], fc[key]), f"{name} ion {i_ion} pcut {k}: {key} differs"
+            assert (ns_o, st_o) == (ns_c, st_c)
+            d = compare_saved(run, sp, eo.get_population(1, n), ec.get_population(1, n), TOL_END_STATE)
+            for kk, v in d.items():
+                worst[kk] = max(worst.get(kk, 0.0), v)
+            if ns_o == 0:
+                break
+            target = inp.n_pts_pcut if pcut < p_hi else inp.n_pts_pcut_hi
+            assert eo.split(target) == ec.split(target)
+            a, b = eo.get_population(0), ec.get_population(0)
+            for nm in abi.POP_I64 + abi.POP_U8:
+                assert np.array_equal(a[nm], b[nm])
+        print(f"\n[{name} ion {i_ion}] worst scaled end-state differences: " +
+              ", ".join(f"{k}={v:.1e}" for k, v in worst.items()))
+        to, tc = eo.end_ion(), ec.end_ion()
+        assert to.stats == tc.stats
+        assert np.array_equal(to.num_crossings, tc.num_crossings)
+        for nm in ("pxx_flux", "pxz_flux", "energy_flux", "esc_psd_feb_upstream", "esc_psd_feb_downstream",
+                   "esc_energy_eff", "esc_num_eff", "weight_coupled", "spectra_coupled", "energy_transfer_pool"):
+            x, y = getattr(to, nm), getattr(tc, nm)
+            assert np.array_equal(x != 0, y != 0), nm
+            assert rel_close(x, y, 0, atol_frac=1e-6) <= TOL_TALLY, nm
+        assert np.array_equal(to.psd != 0, tc.psd != 0) and rel_close(to.psd, tc.psd, 0) <= TOL_TALLY
+        for kk, v in to.scalars.items():
+            assert tc.scalars[kk] == pytest.approx(v, rel=1e-10, abs=0.0)
+        lo, lc = sorted_log(to), sorted_log(tc)
+        assert np.array_equal(lo[0], lc[0])
+        for x, y in zip(lo[1:], lc[1:]):
+            assert rel_close(x, y, 0) <= 1e-8
+        pool = pool + to.energy_transfer_pool
+
+
+def _record_stream(olib, run, i_iter, i_ion, i_pcut, first_global, n_draws, margin=8):
+    """The 'reference random stream' as a recorded array: per particle, the uniforms its private generator
+    would produce (with Julia one dumps rand(Xoshiro(iseed_mod), K); here the stream is Philox)."""
+    olib.mcso_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_double)]
+    off = np.zeros(len(n_draws) + 1, np.int64)
+    off[1:] = np.cumsum(n_draws + margin)
+    u = np.zeros(off[-1])
+    for i, k in enumerate(n_draws + margin):
+        buf = (C.c_double * int(k))()
+        olib.mcso_philox(210, first_global + i, (i_pcut & 0xFFFF) | (i_ion << 16), i_iter, int(k), buf)
+        u[off[i]:off[i + 1]] = np.frombuffer(buf, dtype=np.float64)
+    return u, off
+
+
+@pytest.mark.parametrize("name", ["planar", "relativistic"])
+def test_replay_mode_trajectories(olib, clib, name):
+    """Feed the same recorded uniform stream to the oracle and to the kernel; compare trajectories pass by pass."""
+    inp = small_inputs()[name]
+    inp.n_pts_inj = 200
+    run = problem.setup_run(inp)
+    sp = run.species[0]
+    # 1. Philox run on the oracle to learn how many uniforms each particle consumes in pcut 2 (acceleration)
+    e0 = make_engine(olib, run)
+    start_ion(e0, run)
+    e0.run_pcut(1, run.pcuts[0], 0.0)
+    e0.split(inp.n_pts_pcut)
+    pop2 = {k: v for k, v in e0.get_population(0).items() if k != "l_save"}
+    n = len(pop2["weight"])
+    e0.run_pcut(2, run.pcuts[1], run.pcuts[0])
+    f_philox = e0.get_fates(n)
+    u, off = _record_stream(olib, run, 1, 1, 2, 0, f_philox["n_draws"])
+    # 2. replay on both engines from the identical pcut-2 population
+    steps = 400
+    idx = np.arange(0, n, max(n // 24, 1))[:24]
+    res = []
+    for lib in (olib, clib):
+        e = make_engine(lib, run, rng_mode=abi.RNG_REPLAY)
+        start_ion(e, run, pop=pop2)
+        e.replay_set_stream(u, off)
+        e.trace_enable(idx, steps)
+        # the driver numbers pcuts from 1; the replay stream makes the counter irrelevant
+        e.run_pcut(2, run.pcuts[1], run.pcuts[0])
+        res.append((e.get_fates(n), e.trace_get(), e.get_population(1, n)))
+    (fo, tro, so), (fc, trc, sc) = res
+    for key in ("fate", "helix_count", "retro_steps", "n_draws"):
+        assert np.array_equal(fo[key], f_philox[key]), "oracle replay != oracle philox: " + key
+        assert np.array_equal(fo[key], fc[key]), key
+    worst = 0.0
+    for a, b in zip(tro, trc):
+        assert len(a) == len(b) and len(a) > 0
+        for key in ("i_grid", "helix_count", "flags", "n_draws"):
+            assert np.array_equal(a[key], b[key]), key
+        sc_ = natural_scales(run, sp, {"ptot_pf": a["ptot_pf"], "x_cm": a["x_cm"], "prp_x_cm": a["prp_x_cm"],
+                                       "weight": a["ptot_pf"], "xn_per": a["ptot_pf"]})
+        for key, s in (("x_cm", sc_["x_cm"]), ("ptot_pf", sc_["ptot_pf"]), ("pb_pf", sc_["ptot_pf"]),
+                       ("phi_rad", 2 * np.pi), ("prp_x_cm", sc_["prp_x_cm"]),
+                       ("acctime_sec", np.maximum(np.abs(a["acctime_sec"]), 1e-300))):
+            err = float(np.max(np.abs(a[key] - b[key]) / s))
+            worst = max(worst, err)
+            assert err <= TOL_REPLAY, f"{key}: {err:.3e} over {len(a)} passes"
+    print(f"\n[{name}] replay: worst scaled trajectory difference over {steps} passes x {len(idx)} particles = {worst:.2e}")
+    compare_saved(run, sp, so, sc, TOL_END_STATE)
+
+
+def test_device_pcut_loop_matches_host_loop(clib):
+    run = problem.setup_run(problem.planar_test_particle_input(2000, momentum_cutoffs=LADDER[:6]))
+    a = driver.main_loops(run, make_engine(clib, run), n_iters=1)[0][0]
+    b = driver.main_loops(run, make_engine(clib, run), n_iters=1, host_pcut_loop=True)[0][0]
+    assert a["n_pcuts_run"] == b["n_pcuts_run"] and np.array_equal(a["n_saved"], b["n_saved"])
+    assert np.array_equal(a["n_used"], b["n_used"]) and a["tallies"].stats == b["tallies"].stats
+    assert rel_close(a["pxx_flux"], b["pxx_flux"], 0) < 1e-12 and rel_close(a["tallies"].psd, b["tallies"].psd, 0) < 1e-11
+
+
+def test_full_size_properties(clib):
+    """BASELINE configs[1] at full size (1e6 particles per pcut): size-independent properties."""
+    n = 1_000_000
+    run = problem.setup_run(problem.planar_test_particle_input(n, momentum_cutoffs=LADDER[:3]))
+    e = make_engine(clib, run, na_cr=1000)          # tiny log: exercises the overflow count
+    pop = start_ion(e, run)
+    n0 = len(pop["weight"])
+    w_in, w_out = pop["weight"].sum(), 0.0
+    ints = []
+    for k, pcut in enumerate(run.pcuts, start=1):
+        m = e.population_size()
+        cur_w = e.get_population(0, m)["weight"]
+        ns, steps = e.run_pcut(k, pcut, run.pcuts[k - 2] if k > 1 else 0.0)
+        f = e.get_fates(m)
+        assert ns == int((f["fate"] == abi.FATE_SAVED).sum()) and steps == int(f["helix_count"].sum() + f["retro_steps"].sum())
+        assert f["helix_count"].max() <= 10_001 and f["fate"].max() <= 4
+        w_out += cur_w[f["fate"] != abi.FATE_SAVED].sum()
+        ints.append((ns, steps, int(f["n_draws"].sum())))
+        if ns == 0:
+            break
+        n_new, n_glob, i_mult = e.split(n)
+        assert i_mult == max(n // ns, 1) and n_new == n_glob == ns * i_mult
+        new_w = e.get_population(0, n_new)["weight"]
+        w_saved = cur_w[f["fate"] == abi.FATE_SAVED].sum()
+        assert new_w.sum() == pytest.approx(w_saved, rel=1e-12)
+    assert w_out + new_w.sum() == pytest.approx(w_in, rel=1e-10)      # every weight ends in exactly one fate
+    t = e.end_ion()
+    assert t.stats["n_errors"] == 0 and t.stats["n_neg_sqrt"] == 0
+    assert t.stats["n_cr_count"] == 1000 and t.stats["n_cr_overflow"] == int(t.num_crossings.sum()) - 1000
+    assert np.all(t.psd >= 0) and np.all(t.pxx_flux >= 0)
+    # thermal particles cross every boundary between the fast-push stop and the grid end at least once
+    assert np.all(t.num_crossings[43:] >= n0)
+    # same seed, second run: integer outcomes are run-to-run deterministic
+    e2 = make_engine(clib, run, na_cr=1000)
+    start_ion(e2, run)
+    ns2, st2 = e2.run_pcut(1, run.pcuts[0], 0.0)
+    assert (ns2, st2) == ints[0][:2]
+
+
+def test_flux_conservation_full_size(clib):
+    """1e6 particles with DSA off: tallied fluxes equal the far-upstream fluxes to 1e-3 (8c-3 at scale)."""
+    run = problem.setup_run(problem.planar_test_particle_input(1_000_000, no_dsa=True, momentum_cutoffs=[1e9]))
+    r = driver.main_loops(run, make_engine(clib, run, na_cr=1000), n_iters=1, want_log=False)[0][0]
+    px, en = r["pxx_flux"] / run.F_px_upstream, r["energy_flux"] / run.F_energy_upstream
+    assert np.all(np.abs(px[43:64] - 1) < 2e-3) and np.all(np.abs(en[43:64] - 1) < 4e-3)
+    assert np.all(np.abs(px[85:99] - 1) < 5e-3) and np.all(np.abs(en[85:99] - 1) < 5e-3)
+
+
+def test_statistical_parity_independent_seeds(olib, clib):
+    """Full-run parity with INDEPENDENT random streams (kernel seed 1 vs oracle seed 2): per-bin chi-square on the
+    shock-frame momentum spectrum summed from the PSD and a two-sample KS test on the saved momenta, both at
+    p > 1e-3.  (With equal seeds the two are trajectory-identical, which the tests above already show.)"""
+    from scipy import stats
+    inp = problem.planar_test_particle_input(12_000, momentum_cutoffs=LADDER[:3])
+    run = problem.setup_run(inp)
+    spec, saved = [], []
+    for lib, seed in ((clib, 1), (olib, 2)):
+        e = make_engine(lib, run, seed=seed, threads=8)
+        pop = problem.init_pop(run, run.profile, 1, np.random.default_rng(seed)).pop
+        start_ion(e, run, pop=pop)
+        e.run_pcut(1, run.pcuts[0], 0.0)
+        e.split(inp.n_pts_pcut)
+        n = e.population_size()
+        e.run_pcut(2, run.pcuts[1], run.pcuts[0])
+        s = e.get_population(1, n)
+        saved.append(s["ptot_pf"][s["l_save"] == 1])
+        f = e.get_fates(n)
+        spec.append((np.bincount(f["fate"], minlength=6), f["helix_count"]))
+    ks = stats.ks_2samp(saved[0], saved[1])
+    assert ks.pvalue > 1e-3, ks
+    ks_h = stats.ks_2samp(spec[0][1], spec[1][1])
+    assert ks_h.pvalue > 1e-3, ks_h
+    table = np.array([spec[0][0][:3], spec[1][0][:3]])
+    table = table[:, table.sum(axis=0) > 0]
+    chi = stats.chi2_contingency(table)
+    assert chi[1] > 1e-3, chi
+
+
+def test_two_gpu_nccl_matches_one_gpu(clib):
+    """Needs 2 visible GPUs (gpurun --gpus 2): both ranks live in this process on two handles/devices."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    run = problem.setup_run(problem.planar_test_particle_input(4000, momentum_cutoffs=LADDER[:4]))
+    one = driver.main_loops(run, make_engine(clib, run), n_iters=1)[0][0]
+    engs = [make_engine(clib, run, device=d) for d in range(2)]
+    uid = engs[0].comm_unique_id()
+    out = [None, None]
+
+    class FakeComm:
+        def __init__(self, r):
+            self.rank, self.world = r, 2
+
+    def work(r):
+        engs[r].comm_init(r, 2, uid)
+        out[r] = driver.main_loops(run, engs[r], n_iters=1, comm=FakeComm(r), device_comm=True)[0][0]
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for r in range(2):
+        assert np.array_equal(out[r]["n_saved"], one["n_saved"]) and out[r]["tallies"].stats["n_fate"] == one["tallies"].stats["n_fate"]
+        assert rel_close(out[r]["pxx_flux"], one["pxx_flux"], 0) < 1e-11
+        assert rel_close(out[r]["tallies"].psd, one["tallies"].psd, 0) < 1e-10
