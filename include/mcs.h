@@ -183,6 +183,7 @@ typedef struct McsTraceRec {
 typedef struct McsTiming {
     double transport_ms; /* sum of transport-kernel durations, CUDA events on the library stream */
     double split_ms, reduce_ms, h2d_ms, d2h_ms, comm_ms;
+    double ion_loop_ms;  /* device time of whole mcs_run_ion calls (transport + split + counts + comm) */
     int64_t transport_launches, other_launches;
 } McsTiming;
 

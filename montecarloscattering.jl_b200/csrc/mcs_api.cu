@@ -96,7 +96,7 @@ struct McsHandle {
     McsSpecies sp;
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
     bool have_profile = false, have_ion = false;
     int i_iter = 0, i_ion = 0;
     int ng = 0, M = 0, T = 0;
@@ -169,6 +169,8 @@ extern "C" int mcs_destroy(McsHandle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
+    if (h->ev4) cudaEventDestroy(h->ev4);
+    if (h->ev5) cudaEventDestroy(h->ev5);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MCS_OK;
@@ -214,7 +216,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
 #define TRY(x) do { rc = (x); if (rc != MCS_OK) { mcs_destroy(h); return rc; } } while (0)
 #define CUA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(MCS_ERR_NOMEM, "CUDA alloc: %s at %s", cudaGetErrorString(e_), #call); mcs_destroy(h); return MCS_ERR_NOMEM; } } while (0)
     CUA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CUA(cudaEventCreate(&h->ev0)); CUA(cudaEventCreate(&h->ev1)); CUA(cudaEventCreate(&h->ev2)); CUA(cudaEventCreate(&h->ev3));
+    CUA(cudaEventCreate(&h->ev0)); CUA(cudaEventCreate(&h->ev1)); CUA(cudaEventCreate(&h->ev2)); CUA(cudaEventCreate(&h->ev3)); CUA(cudaEventCreate(&h->ev4)); CUA(cudaEventCreate(&h->ev5));
     const int ng = h->ng, ng2 = ng + 2;
     const long long N = cfg->n_pts_max;
     CUA(cudaMalloc(&h->d_grid, (size_t)(9 * ng2 + MCS_NA_C) * 8));
@@ -514,6 +516,8 @@ extern "C" int mcs_run_ion(McsHandle* h, const double* pcuts, int32_t n_pcuts, d
                            int64_t n_pts_pcut_hi, int32_t* n_run, int64_t* n_used, int64_t* n_saved_arr) {
     if (!h || !pcuts || n_pcuts < 1 || n_pcuts > MCS_NA_C) return fail(MCS_ERR_ARG, "bad pcuts");
     int32_t k = 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev4, h->stream));
     for (int32_t i = 1; i <= n_pcuts; i++) {
         int64_t ns = 0, nst = 0;
         long long used_g = 0;
@@ -540,6 +544,11 @@ extern "C" int mcs_run_ion(McsHandle* h, const double* pcuts, int32_t n_pcuts, d
             if (rc) return rc;
         }
     }
+    CU(cudaEventRecord(h->ev5, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms_loop = 0;
+    CU(cudaEventElapsedTime(&ms_loop, h->ev4, h->ev5));
+    h->tm.ion_loop_ms += ms_loop;
     if (n_run) *n_run = k;
     return MCS_OK;
 }

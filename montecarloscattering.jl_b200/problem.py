@@ -46,6 +46,11 @@ DEFAULT_PCUTS = [
     5.623e11, 1.000e12, 1.778e12, 3.162e12, 5.623e12, 1.000e13,
 ]  # mc_in.toml:84-130
 
+# Cut-offs for the non-relativistic configs [m_p c]. The bundled list was written for gamma0 = 5: at
+# u0 = 1e4 km/s it leaves ONE wide pcut (0.01 -> 0.6 m_p c) below the FEB-limited maximum (~0.6 m_p c), i.e. no
+# splitting at all; this ladder splits every factor ~1.5 so each pcut holds its target population.
+NONREL_PCUTS = [0.01, 0.04, 0.06, 0.09, 0.13, 0.2, 0.3, 0.45, 0.6, 1.0, 1.6, 2.5]
+
 
 @dataclass
 class ShockInput:
@@ -118,6 +123,7 @@ def planar_test_particle_input(n_per_pcut: int = 1_000_000, **kw) -> ShockInput:
         denz_ion=[1.0], n_pts_inj=n_per_pcut, n_pts_pcut=n_per_pcut, n_pts_pcut_hi=n_per_pcut, no_scatter=False,
         no_dsa=False, use_retro=True, tcuts=None, maximum_age=-1.0, energy_transfer_frac=0.0,
         b_field_turbulence=0.0, use_custom_epsB=False, radiation_losses=False, smooth_shocks=False,
+        momentum_cutoffs=list(NONREL_PCUTS),
     )
     d.update(kw)
     return ShockInput(**d)
@@ -132,7 +138,7 @@ def nonlinear_input(n_per_pcut: int = 10_000_000, **kw) -> ShockInput:
 
 def relativistic_input(n_per_pcut: int = 1_000_000, **kw) -> ShockInput:
     """config 3: upstream Lorentz factor 10."""
-    d = dict(shock_speed=10.0, shock_speed_unit="gamma")
+    d = dict(shock_speed=10.0, shock_speed_unit="gamma", momentum_cutoffs=list(DEFAULT_PCUTS))
     d.update(kw)
     return planar_test_particle_input(n_per_pcut, **d)
 
@@ -142,7 +148,7 @@ def multi_species_input(n_per_pcut: int = 10_000_000, **kw) -> ShockInput:
     d = dict(
         shock_speed=1.5, shock_speed_unit="gamma", aa_ion=[1.0, 4.0, float("nan")], zz_ion=[1.0, 2.0, -1.0],
         tz_ion=[1e6, 1e6, 1e6], denz_ion=[1.0, 0.1, 1.2], radiation_losses=True, energy_transfer_frac=0.1,
-        fast_upstream_transport=True,
+        fast_upstream_transport=True, momentum_cutoffs=list(DEFAULT_PCUTS),
     )
     d.update(kw)
     return planar_test_particle_input(n_per_pcut, **d)
@@ -568,30 +574,28 @@ def set_inj_dist(inj_weight: bool, n_pts_inj: int, inp_distr: int, T_or_E: float
     area_tot = 0.0
     for a in areas:
         area_tot += a
-    ptot, weight = [], []
+    centres = np.array([math.sqrt(p_range[i] * p_range[i + 1]) for i in range(nb)])
     if inj_weight:
         area_per_pt = area_tot / n_pts_inj
+        counts = np.array([int(np.round(a / area_per_pt)) for a in areas])  # Julia round(Int, x): ties to even
+        ptot = np.repeat(centres, counts)
         if compat_zero_first:  # `n_pts_tot = 1` at :1425 leaves slot 1 at ptot = 0 (SURVEY B-7)
-            ptot.append(0.0)
-        for i in range(nb):
-            k = int(np.round(areas[i] / area_per_pt))  # Julia round(Int, x): ties to even, like numpy
-            ptot += [math.sqrt(p_range[i] * p_range[i + 1])] * k
+            ptot = np.concatenate(([0.0], ptot))
         n = len(ptot)
-        weight = [n0 / n] * n
+        weight = np.full(n, n0 / n)
     else:
         n_per_bin = n_pts_inj // nb
         if n_per_bin < 5:
             raise ValueError("too few particles per bin; increase n_pts_inj")
-        for i in range(nb):
-            ptot += [math.sqrt(p_range[i] * p_range[i + 1])] * n_per_bin
-            weight += [areas[i] / area_tot / n_per_bin * n0] * n_per_bin
+        ptot = np.repeat(centres, n_per_bin)
+        weight = np.repeat(np.array([a / area_tot / n_per_bin * n0 for a in areas]), n_per_bin)
     n_tot = len(ptot)
     if inp_distr == 2:
         E_inj = T_or_E * KEV
         p = math.sqrt(2 * m * E_inj) if E_inj / E0 < E_REL_PT else math.sqrt(E_inj**2 - E0**2) / CL
-        ptot = [p] * n_pts_inj
-        weight = [n0 / n_tot] * n_pts_inj
-    return np.array(ptot, float), np.array(weight, float)
+        ptot = np.full(n_pts_inj, p)
+        weight = np.full(n_pts_inj, n0 / n_tot)
+    return np.asarray(ptot, float), np.asarray(weight, float)
 
 
 @dataclass

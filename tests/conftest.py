@@ -22,6 +22,11 @@ def olib():
 
 @pytest.fixture(scope="session")
 def clib():
-    """CUDA library (the product). Fails loudly if it has not been built."""
+    """CUDA library (the product). Fails loudly if it has not been built.
+    MCS_TEST_LOGIC_ONLY=1 substitutes the oracle so the TEST LOGIC of the gpu-marked tests can be debugged on a
+    box without a GPU; such a run proves nothing about the kernel and is never what the driver runs."""
+    if os.environ.get("MCS_TEST_LOGIC_ONLY") == "1":
+        import oracle_engine
+        return oracle_engine.load_oracle_library()
     import mcs_b200
     return mcs_b200.load_cuda_library()
