@@ -111,7 +111,8 @@ typedef struct McsConfig {
     uint32_t compat;
     int32_t rng_mode;
     int32_t threads;    /* CPU oracle only: OpenMP threads (0/1 = serial, ordered) */
-    int32_t reserved;
+    int32_t dynamic_queue; /* 0 = particles dealt to warps in a fixed interleaved order (run-to-run deterministic tallies);
+                              1 = global atomic work queue (load-balanced, summation order varies) */
 } McsConfig;
 
 /* Per-species scalars read inside the loop (main_loops.jl:97-100, utils.jl:72-96). */

@@ -50,7 +50,7 @@ class McsConfig(C.Structure):
         ("do_rad_losses", _i32), ("do_retro", _i32), ("do_tcuts", _i32), ("dont_DSA", _i32),
         ("dont_scatter", _i32), ("use_custom_frg", _i32), ("use_custom_epsB", _i32),
         ("helix_cap", _i32), ("retro_cap", _i64), ("seed", _u64), ("compat", _u32),
-        ("rng_mode", _i32), ("threads", _i32), ("reserved", _i32),
+        ("rng_mode", _i32), ("threads", _i32), ("dynamic_queue", _i32),
     ]
 
 

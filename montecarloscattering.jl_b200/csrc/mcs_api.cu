@@ -184,7 +184,7 @@ static int env_int(const char* name, int dflt) {
 extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     if (!cfg || !out) return fail(MCS_ERR_ARG, "null argument");
     if (cfg->abi_version != MCS_ABI_VERSION) return fail(MCS_ERR_ARG, "abi_version mismatch");
-    if (cfg->n_grid < 1 || cfg->n_grid > 1536 || cfg->n_pts_max < 1 || cfg->n_ions < 1 || cfg->n_ions > MCS_MAX_IONS ||
+    if (cfg->n_grid < 1 || cfg->n_grid > 2048 || cfg->n_pts_max < 1 || cfg->n_ions < 1 || cfg->n_ions > MCS_MAX_IONS ||
         cfg->n_tcuts > MCS_NA_C || cfg->n_tcuts < 0 || cfg->n_xspec > MCS_MAX_XSPEC || cfg->n_xspec < 0 ||
         cfg->num_psd_mom_bins < 1 || cfg->num_psd_theta_bins < 1 || cfg->na_cr < 0)
         return fail(MCS_ERR_ARG, "bad sizes in McsConfig");
@@ -209,8 +209,9 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, dev));
     h->n_sm = prop.multiProcessorCount;
-    h->block = env_int("MCS_BLOCK", 256);
-    h->blocks_per_sm = env_int("MCS_BLOCKS_PER_SM", 2);
+    h->block = env_int("MCS_BLOCK", MCS_BLOCK);
+    if (h->block > MCS_BLOCK || h->block < 32 || (h->block & 31)) h->block = MCS_BLOCK;
+    h->blocks_per_sm = env_int("MCS_BLOCKS_PER_SM", MCS_MIN_BLOCKS);
     h->max_blocks = h->n_sm * h->blocks_per_sm;
     int rc = MCS_OK;
 #define TRY(x) do { rc = (x); if (rc != MCS_OK) { mcs_destroy(h); return rc; } } while (0)
@@ -240,12 +241,18 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     CUA(cudaMalloc(&h->d_u64, (size_t)(ng + CNT_N) * 8));
     const size_t L = (size_t)(cfg->na_cr > 0 ? cfg->na_cr : 1);
     CUA(cudaMalloc(&h->d_tg, L * 8)); CUA(cudaMalloc(&h->d_tpx, L * 8)); CUA(cudaMalloc(&h->d_tpt, L * 8)); CUA(cudaMalloc(&h->d_tw, L * 8));
-    CUA(cudaMalloc(&h->d_partials, (size_t)h->max_blocks * 4 * ng * 8));
+    CUA(cudaMalloc(&h->d_partials, (size_t)h->max_blocks * (4 * ng + SC_N) * 8));
     CUA(cudaMalloc(&h->d_gather, 64 * 8));
     CUA(cudaMemsetAsync(h->d_tally, 0, o * 8, h->stream));
     CUA(cudaMemsetAsync(h->d_u64, 0, (size_t)(ng + CNT_N) * 8, h->stream));
-    CUA(cudaFuncSetAttribute(transport_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ng * 8));
-    CUA(cudaFuncSetAttribute(transport_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ng * 8));
+    while (h->block > 32 && (size_t)(h->block / 32) * warp_smem_bytes(ng) > (size_t)100 * 1024) h->block /= 2;
+    {
+        const int smem = (int)((size_t)(h->block / 32) * warp_smem_bytes(ng));
+        CUA(cudaFuncSetAttribute(transport_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUA(cudaFuncSetAttribute(transport_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUA(cudaFuncSetAttribute(transport_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUA(cudaFuncSetAttribute(transport_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
 #undef TRY
 #undef CUA
     // static part of the kernel parameters
@@ -264,7 +271,16 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     P.n_tcuts = cfg->n_tcuts; P.helix_cap = cfg->helix_cap; P.retro_cap = cfg->retro_cap;
     P.flags = (cfg->do_rad_losses ? F_RAD_LOSSES : 0) | (cfg->do_retro ? F_RETRO : 0) | (cfg->do_tcuts ? F_TCUTS : 0) |
               (cfg->dont_DSA ? F_DONT_DSA : 0) | (cfg->dont_scatter ? F_DONT_SCATTER : 0) |
-              (cfg->use_custom_epsB ? F_CUSTOM_EPSB : 0) | ((cfg->compat & MCS_COMPAT_RETRO_KEEP_NEW_PITCH) ? F_KEEP_NEW_PITCH : 0);
+              (cfg->use_custom_epsB ? F_CUSTOM_EPSB : 0) | ((cfg->compat & MCS_COMPAT_RETRO_KEEP_NEW_PITCH) ? F_KEEP_NEW_PITCH : 0) |
+              ((cfg->dynamic_queue || env_int("MCS_DYNAMIC_QUEUE", 0)) ? F_DYNAMIC_QUEUE : 0);
+    {   // per-xn_per scattering constants, host libm (scattering.jl:46-60: the gyroradius cancels in vp_tg / lambda_mfp)
+        const double xn[2] = {cfg->xn_per_fine, cfg->xn_per_coarse};
+        for (int k = 0; k < 2; k++) {
+            P.omc[k] = 1 - cos(sqrt(6 * (TWO_PI * 1.0) / (xn[k] * (cfg->eta_mfp * 1.0))));
+            P.inv_xn[k] = 1.0 / xn[k];
+            P.dphi[k] = TWO_PI / xn[k];
+        }
+    }
     P.key0 = (uint32_t)cfg->seed; P.key1 = (uint32_t)(cfg->seed >> 32);
     double* g = h->d_grid;
     P.xg = g; P.ux = g + ng2; P.uz = g + 2 * ng2; P.ut = g + 3 * ng2; P.gsf = g + 4 * ng2; P.gef = g + 5 * ng2;
@@ -275,7 +291,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     double* b = h->d_tally;
     t.psd = b + h->off_psd; t.esc_up = b + h->off_esc_up; t.esc_dn = b + h->off_esc_dn; t.esc_en_eff = b + h->off_en_eff;
     t.esc_num_eff = b + h->off_num_eff; t.w_coupled = b + h->off_wc; t.s_coupled = b + h->off_sc; t.pool = b + h->off_pool;
-    t.spec_sf = b + h->off_sf; t.spec_pf = b + h->off_pf; t.scalars = b + h->off_scal;
+    t.spec_sf = b + h->off_sf; t.spec_pf = b + h->off_pf;
     t.counters = h->d_u64 + ng;
     t.tg = h->d_tg; t.tpx = h->d_tpx; t.tpt = h->d_tpt; t.tw = h->d_tw; t.na_cr = cfg->na_cr;
     t.block_partials = h->d_partials;
@@ -415,15 +431,21 @@ extern "C" int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pc
     if (n > 0) {
         long long want = (n + h->block - 1) / h->block;
         int blocks = (int)(want < h->max_blocks ? want : h->max_blocks);
-        size_t smem = (size_t)4 * h->ng * 8;
+        size_t smem = (size_t)(h->block / 32) * warp_smem_bytes(h->ng);
+        const bool electron = h->sp.aa < 1;
         CU(cudaEventRecord(h->ev0, h->stream));
-        if (debug) transport_kernel<true><<<blocks, h->block, smem, h->stream>>>(P);
-        else transport_kernel<false><<<blocks, h->block, smem, h->stream>>>(P);
+        if (debug) {
+            if (electron) transport_kernel<true, true><<<blocks, h->block, smem, h->stream>>>(P);
+            else transport_kernel<true, false><<<blocks, h->block, smem, h->stream>>>(P);
+        } else {
+            if (electron) transport_kernel<false, true><<<blocks, h->block, smem, h->stream>>>(P);
+            else transport_kernel<false, false><<<blocks, h->block, smem, h->stream>>>(P);
+        }
         CU(cudaEventRecord(h->ev1, h->stream));
         CU(cudaGetLastError());
         double* b = h->d_tally;
-        reduce_partials_kernel<<<(4 * h->ng + 127) / 128, 128, 0, h->stream>>>(h->d_partials, blocks, h->ng, b + h->off_pxx,
-                                                                             b + h->off_pxz, b + h->off_efl, h->d_u64);
+        reduce_partials_kernel<<<(4 * h->ng + SC_N + 127) / 128, 128, 0, h->stream>>>(
+            h->d_partials, blocks, h->ng, b + h->off_pxx, b + h->off_pxz, b + h->off_efl, h->d_u64, b + h->off_scal);
         CU(cudaGetLastError());
         h->tm.transport_launches++; h->tm.other_launches++;
     }

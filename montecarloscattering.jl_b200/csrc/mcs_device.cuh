@@ -1,19 +1,37 @@
 // mcs_device.cuh — device side of the B200 transport loop (sm_100a).
 //
-// One persistent kernel advances a whole pcut's population: every lane owns one particle at a time,
-// runs helix-loop passes (reference src/particle_loop.jl:154-499) until the particle is saved, escapes
-// or is lost, tallies it (src/particle_finish.jl:46-107) and claims the next particle from a global
-// queue with one warp-aggregated atomic per refill.  Nothing returns to the host within a pcut.
+// One persistent kernel advances a whole pcut's population (reference src/particle_loop.jl:154-499 +
+// src/particle_finish.jl:46-107).  Design, driven by the ncu evidence in profiles/:
 //
-// This is FP64 scalar work with data-dependent control flow: no dense contraction, so no tensor
-// cores / TMA; the levers are FP64-pipe issue efficiency, warp occupancy of the lanes (refill), and
-// where the tallies live (shared memory per block for the n_grid-sized flux arrays, L2 atomics for the
-// 22 MB phase-space histogram).
+//  * every lane owns one particle at a time and runs helix-loop passes; idle lanes are refilled from a
+//    per-warp interleaved sequence (deterministic) or a global atomic queue (dynamic);
+//  * the per-pass HOT path (scatter, move, zone test) is kept compact; everything rare (zone change boost,
+//    energy transfer, retro_time, reflection, PRP logic) is out of line so the loop fits the instruction cache;
+//  * work that only a few lanes need in a given pass — zone-boundary flux/PSD tallies (all_flux.jl) and the
+//    escape tallies (particle_finish.jl) — is NOT done in place: the lane appends a 64-byte event to a
+//    per-warp queue in shared memory and the warp processes events 32 at a time, fully converged;
+//  * the n_grid-sized flux tallies and the scalars are accumulated per warp in shared memory with plain
+//    adds in a fixed order (no FP64 atomics: on sm_100a shared FP64 atomicAdd is a CAS loop), then reduced
+//    over warps and blocks in a fixed order -> run-to-run deterministic;
+//  * the 22 MB phase-space histogram lives in L2/HBM and takes red.global.add.f64.
+//
+// FP64 scalar work with data-dependent control flow: no dense contraction, so no tensor cores / TMA.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "../../include/mcs.h"
+#include "mcs_math.cuh"
+
+#define MCS_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define MCS_LIKELY(x) __builtin_expect(!!(x), 1)
+
+#ifndef MCS_BLOCK
+#define MCS_BLOCK 256
+#endif
+#ifndef MCS_MIN_BLOCKS
+#define MCS_MIN_BLOCKS 2
+#endif
 
 namespace mcs {
 
@@ -24,17 +42,30 @@ constexpr double HALF_PI = PI / 2;
 constexpr double SIN_UPPER_LIMIT = 0.99999999999999989;  // prevfloat(1.0), scattering.jl:3
 constexpr double SPIKE_AWAY = 1000.0;                    // all_flux.jl:4, particle_finish.jl:5
 constexpr int E1 = MCS_PSD_MAX + 1;
+constexpr int QCAP = 64;  // per-warp event queue: < 32 left after a drain + at most 1 event per lane per push point
+constexpr unsigned FULL = 0xffffffffu;
 
 enum : uint32_t {
     F_RAD_LOSSES = 1u, F_RETRO = 2u, F_TCUTS = 4u, F_DONT_DSA = 8u, F_DONT_SCATTER = 16u, F_CUSTOM_EPSB = 32u,
-    F_KEEP_NEW_PITCH = 64u,
+    F_KEEP_NEW_PITCH = 64u, F_DYNAMIC_QUEUE = 128u,
 };
 
-// SoA particle record (main_loops.jl:212-226)
-struct PopPtrs {
+// event flags
+enum : uint32_t {
+    EV_VALID = 1u, EV_FINISH = 2u, EV_INJ = 4u, EV_UP = 8u, EV_FEB_UP = 16u, EV_SUMP = 32u,
+    EV_REASON_SHIFT = 8, EV_XSPEC_SHIFT = 16,
+};
+
+struct PopPtrs {  // SoA particle record (main_loops.jl:212-226)
     double *weight, *ptot, *pb, *x, *xn_per, *prp_x, *acctime, *phi;
     long long *grid, *tcut;
     uint8_t *down, *inj;
+};
+
+enum { SC_ESC_FLUX = 0, SC_PX_ESC_FEB, SC_EN_ESC_FEB, SC_SUMP, SC_SUMKE, SC_PX_ESC_UP, SC_EN_ESC_UP, SC_N = 8 };
+enum {
+    CNT_HELIX = 0, CNT_RETRO, CNT_W_PPERP, CNT_W_PSDMOM, CNT_NEGSQRT, CNT_RETRO_CAP, CNT_ERR, CNT_FATE0,  // ..FATE5 = 12
+    CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_N = 24
 };
 
 struct TallyPtrs {
@@ -48,20 +79,11 @@ struct TallyPtrs {
     double* pool;           // [n_grid]
     double* spec_sf;        // [E1*MAX_XSPEC]
     double* spec_pf;
-    double* scalars;        // [8]: esc_flux, px_esc_feb, en_esc_feb, sumP, sumKE, px_esc_up, en_esc_up
-    unsigned long long* counters;  // [16] see CNT_*
-    // thermal-crossing log
-    long long* tg;
+    unsigned long long* counters;  // [CNT_N]
+    long long* tg;          // thermal-crossing log
     double *tpx, *tpt, *tw;
     long long na_cr;
-    // per-block partials of the n_grid-sized tallies: [gridDim.x][4*n_grid] (pxx, pxz, efl, crossings-as-bits)
-    double* block_partials;
-};
-
-enum { SC_ESC_FLUX = 0, SC_PX_ESC_FEB, SC_EN_ESC_FEB, SC_SUMP, SC_SUMKE, SC_PX_ESC_UP, SC_EN_ESC_UP, SC_N = 8 };
-enum {
-    CNT_HELIX = 0, CNT_RETRO, CNT_W_PPERP, CNT_W_PSDMOM, CNT_NEGSQRT, CNT_RETRO_CAP, CNT_ERR, CNT_FATE0,  // ..FATE5 = 12
-    CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_N = 24
+    double* block_partials; // [gridDim.x][4*n_grid + SC_N]: pxx | pxz | efl | crossings (u64 bits) | scalars
 };
 
 struct DevParams {
@@ -69,6 +91,8 @@ struct DevParams {
     double mp, c, qcgs, E_rel_pt, rad_loss_fac, gam0, u0, u2, bmag2, pe_crit, gam_e_crit, eta_mfp;
     double psd_mom_min, psd_cos_fine, delta_cos, psd_theta_min, bpd_mom, bpd_th;
     double energy_transfer_frac, feb_up, feb_dn, x_grid_stop, B_CMBz, xn_fine, xn_coarse, age_max;
+    // per-xn_per scattering constants, [0] fine [1] coarse: 1-cos_max (scattering.jl:46-60), 1/xn_per, 2pi/xn_per
+    double omc[2], inv_xn[2], dphi[2];
     double x_spec[MCS_MAX_XSPEC];
     int M, T, n_grid, i_grid_feb, i_shock, n_xspec, n_tcuts, helix_cap;
     long long retro_cap;
@@ -97,7 +121,42 @@ struct DevParams {
     int trace_max;
 };
 
+__host__ __device__ inline size_t warp_smem_bytes(int ng) {
+    return (size_t)(4 * ng + SC_N) * 8 + (size_t)QCAP * (6 * 8 + 4 * 4);
+}
+
+// per-warp shared-memory view
+struct WarpMem {
+    double* part;  // [4*ng + SC_N]: pxx | pxz | efl | crossings(u64) | scalars
+    double *q_pb, *q_pperp, *q_gam, *q_phi, *q_w, *q_ptot;
+    int *q_inew, *q_iold, *q_iz;
+    uint32_t* q_flags;
+};
+
+__device__ __forceinline__ WarpMem warp_mem(unsigned char* base, int warp, int ng) {
+    WarpMem w;
+    unsigned char* p = base + (size_t)warp * warp_smem_bytes(ng);
+    w.part = reinterpret_cast<double*>(p);
+    double* q = w.part + 4 * ng + SC_N;
+    w.q_pb = q; w.q_pperp = q + QCAP; w.q_gam = q + 2 * QCAP; w.q_phi = q + 3 * QCAP; w.q_w = q + 4 * QCAP;
+    w.q_ptot = q + 5 * QCAP;
+    int* qi = reinterpret_cast<int*>(q + 6 * QCAP);
+    w.q_inew = qi; w.q_iold = qi + QCAP; w.q_iz = qi + 2 * QCAP;
+    w.q_flags = reinterpret_cast<uint32_t*>(qi + 3 * QCAP);
+    return w;
+}
+
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void count(const DevParams& P, int which, unsigned long long v = 1ull) {
+    red_add_u64(&P.t.counters[which], v);
+}
+
 // RNG: Philox4x32-10, counter = (block, i_prt, i_pcut | i_ion<<16, i_iter), key = seed. Replaces the
 // per-particle Random.Xoshiro(iseed_mod) of particle_loop.jl:34-41.  Integer pipe only.
 struct Rng {
@@ -140,15 +199,41 @@ __device__ __forceinline__ double uniform(Rng& g, const DevParams& P) {
     return u53(g.s3, g.s2);
 }
 
+// two consecutive uniforms; one Philox block when the stream is block-aligned (the common case)
+template <bool DEBUG>
+__device__ __forceinline__ void uniform2(Rng& g, const DevParams& P, double& a, double& b) {
+    if ((DEBUG && g.ru != nullptr) || (g.n & 1u)) {
+        a = uniform<DEBUG>(g, P);
+        b = uniform<DEBUG>(g, P);
+        return;
+    }
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10(g.n >> 1, g.c1, P.ctr2, P.ctr3, P.key0, P.key1, o0, o1, o2, o3);
+    g.n += 2; g.s2 = o2; g.s3 = o3;
+    a = u53(o1, o0);
+    b = u53(o3, o2);
+}
+
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mod2pi(double x) {  // Base.mod2pi semantics (SURVEY App. E)
-    if (x >= 0.0 && x < TWO_PI) return x;
+__device__ __noinline__ double mod2pi_slow(double x) {
     double k = floor(x / TWO_PI);
     double r = fma(-k, TWO_PI, x);
     r = r - k * TWO_PI_LO;
     if (r < 0.0) r += TWO_PI;
     if (r >= TWO_PI) r -= TWO_PI;
     return r;
+}
+__device__ __forceinline__ double mod2pi(double x) {  // Base.mod2pi semantics (SURVEY App. E)
+    if (x >= 0.0 && x < TWO_PI) return x;
+    if (x >= TWO_PI && x < 2 * TWO_PI) {  // k = 1 of the general formula, same roundings
+        double r = (x - TWO_PI) - TWO_PI_LO;
+        return r < 0.0 ? r + TWO_PI : r;
+    }
+    if (x < 0.0 && x > -TWO_PI) {  // k = -1 (phase is negative after a boost or a scattering)
+        double r = (x + TWO_PI) + TWO_PI_LO;
+        return r >= TWO_PI ? r - TWO_PI : r;
+    }
+    return mod2pi_slow(x);
 }
 
 __device__ __forceinline__ double norm3(double x, double y, double z) {
@@ -162,12 +247,8 @@ __device__ __forceinline__ double norm3(double x, double y, double z) {
     return sqrt(s);
 }
 
-__device__ __forceinline__ void count(const DevParams& P, int which, unsigned long long v = 1ull) {
-    atomicAdd(&P.t.counters[which], v);
-}
-
 __device__ __forceinline__ double sqrt_guard(const DevParams& P, double a) {
-    if (a < 0.0) { count(P, CNT_NEGSQRT); return 0.0; }
+    if (MCS_UNLIKELY(a < 0.0)) { count(P, CNT_NEGSQRT); return 0.0; }
     return sqrt(a);
 }
 
@@ -198,7 +279,7 @@ __device__ __forceinline__ void transform_p_PS(const DevParams& P, double pb, do
                                                double ux, double gsf, double bcos, double bsin, double& ptot_sk,
                                                double& sx, double& sz, double& gam_sk) {
     double sp, cp;
-    sincos(phi + HALF_PI, &sp, &cp);
+    sincos_bf(phi + HALF_PI, &sp, &cp);
     double p_p_cos = pperp * cp;
     double fx = pb * bcos - p_p_cos * bsin;
     double fy = pperp * sp;
@@ -208,6 +289,14 @@ __device__ __forceinline__ void transform_p_PS(const DevParams& P, double pb, do
     sz = fz;
     ptot_sk = norm3(sx, fy, sz);
     gam_sk = hypot(ptot_sk / P.mc, 1.0);
+}
+
+// pmax test of particle_loop.jl:262-275 (cold: only above pmax_cutoff)
+__device__ __noinline__ bool above_pmax_shock_frame(const DevParams& P, double pb, double pperp, double gam_pf, double phi,
+                                                    int iz) {
+    double ptot_sk, sx, sz, gam_sk;
+    transform_p_PS(P, pb, pperp, gam_pf, phi, P.ux[iz], P.gsf[iz], P.costh[iz], P.sinth[iz], ptot_sk, sx, sz, gam_sk);
+    return ptot_sk > P.pmax_cutoff;
 }
 
 // transformers.jl:523-607; zone `io` -> shock frame -> zone `in`
@@ -260,9 +349,9 @@ __device__ __forceinline__ double radiation_loss(const DevParams& P, double B2, 
 
 // cuts.jl:149-162
 __device__ __noinline__ void tcut_track(const DevParams& P, int tcut_curr, double weight, double ptot) {
-    atomicAdd(&P.t.w_coupled[tcut_curr - 1], weight);
+    red_add_f64(&P.t.w_coupled[tcut_curr - 1], weight);
     int ip = psd_bin_momentum(P, ptot);
-    atomicAdd(&P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
+    red_add_f64(&P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
 }
 
 // particle_loop.jl:652-723
@@ -284,7 +373,7 @@ __device__ __noinline__ void do_energy_transfer(const DevParams& P, int i_grid, 
         for (int i = i_start + 1; i <= i_stop; i++) n_split += P.eps_target[i - 1] > 0;
         double inc = (gam_i - gam_f) * E0 * weight / n_split;
         for (int i = i_start + 1; i <= i_stop; i++)
-            if (P.eps_target[i - 1] > 0) atomicAdd(&P.t.pool[i - 1], inc);
+            if (P.eps_target[i - 1] > 0) red_add_f64(&P.t.pool[i - 1], inc);
         scale = true;
     } else if (rmax > 0) {
         double sum = 0.0;
@@ -300,8 +389,8 @@ __device__ __noinline__ void do_energy_transfer(const DevParams& P, int i_grid, 
     }
 }
 
-// prob_return.jl:217-344.  Runs as a nested loop on the lane: retro passes are ~1e-3 of all passes.
-template <bool DEBUG>
+// prob_return.jl:217-344.  Nested loop on the lane: retro passes are ~1e-3 of all passes.
+template <bool DEBUG, bool ELECTRON>
 __device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd, double prp_x, double& ptot,
                                         double& pb, double& pperp, double& gam_pf, double& acct, double weight,
                                         int& tcut_curr, double& phi_out, long long& n_steps) {
@@ -342,7 +431,7 @@ __device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd
         phi = TWO_PI * uniform<DEBUG>(rng, P);
         pb = (2 * uniform<DEBUG>(rng, P) - 1) * ptot;
         pperp = sqrt_guard(P, ptot * ptot - pb * pb);
-        if ((P.flags & F_RAD_LOSSES) && P.aa < 1) ptot = radiation_loss(P, B2, ptot, t_step);
+        if (ELECTRON && (P.flags & F_RAD_LOSSES)) ptot = radiation_loss(P, B2, ptot, t_step);
         if (ptot <= 0) {
             ptot = 1.0e-99; gam_pf = 1.0; lose = true;
             break;
@@ -353,7 +442,7 @@ __device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd
         } else {
             pb = ptot * cos_old; pperp = ptot * sin_old;
         }
-        gam_pf = hypot(1.0, ptot / P.mc);
+        if (ELECTRON) gam_pf = hypot(1.0, ptot / P.mc);  // ions: ptot is unchanged, hypot returns the same bits
         if (x < prp_x) break;
         if (steps >= P.retro_cap) { count(P, CNT_RETRO_CAP); break; }
     }
@@ -362,151 +451,288 @@ __device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd
     return lose;
 }
 
-// particle_finish.jl:46-107 with the zone values the loop last loaded (particle_loop.jl:503-507)
-__device__ __noinline__ void particle_finish(const DevParams& P, int reason, double pb, double pperp, double gam_pf,
-                                             double phi, double ux, double gsf, double bcos, double bsin,
-                                             double weight) {
-    double E0 = P.m * (P.c * P.c);
+// ---------------------------------------------------------------------------------------------
+// Process up to 32 queued events, one per lane, fully converged:
+//   crossing event -> all_flux.jl:86-158 (transform to the shock frame, flux / PSD / thermal-log tallies, x_spec spectra,
+//                     upstream-FEB scalars);
+//   finish event   -> particle_finish.jl:46-107 and the downstream sums of particle_loop.jl:478-495.
+// The n_grid-sized tallies and the scalars go to this warp's shared partials with plain adds in event order.
+__device__ __noinline__ void process_events(const DevParams& P, const WarpMem& wm, int base, int n_ev) {
+    const int lane = threadIdx.x & 31, ng = P.n_grid;
+    const bool act = lane < n_ev;
+    const int q = base + (act ? lane : 0);
+    const uint32_t fl = act ? wm.q_flags[q] : 0u;
+    const double pb = wm.q_pb[q], pperp = wm.q_pperp[q], gam_pf = wm.q_gam[q], phi = wm.q_phi[q], weight = wm.q_w[q],
+                 ptot = wm.q_ptot[q];
+    const int i_new = wm.q_inew[q], i_old = wm.q_iold[q], iz = wm.q_iz[q];
+    const double ux = P.ux[iz], gsf = P.gsf[iz], bcos = P.costh[iz], bsin = P.sinth[iz];
     double ptot_sk, sx, sz, gam_sk;
     transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
-    int ip = min(psd_bin_momentum(P, ptot_sk), MCS_PSD_MAX), jt = min(psd_bin_angle(P, sx, ptot_sk), MCS_PSD_MAX);
-    double wf;
-    if (ptot_sk > fabs(SPIKE_AWAY * sx)) wf = gam_sk * P.m * SPIKE_AWAY / ptot_sk;
-    else wf = gam_sk * (P.m / fabs(sx));
-    if (reason == 1) {
-        atomicAdd(&P.t.esc_dn[ip + E1 * jt], weight * wf);
-    } else if (reason == 2) {
-        atomicAdd(&P.t.scalars[SC_ESC_FLUX], weight);
-        atomicAdd(&P.t.esc_up[ip + E1 * jt], weight * wf);
-        bool rel = (gam_sk - 1) >= P.E_rel_pt;  // F-8
-        double Ek = rel ? (gam_sk - 1) * E0 : ptot_sk * ptot_sk / (2 * P.m);
-        double en_add = Ek * weight;
-        atomicAdd(&P.t.scalars[SC_PX_ESC_FEB], fabs(sx) * weight);
-        atomicAdd(&P.t.scalars[SC_EN_ESC_FEB], en_add);
-        atomicAdd(&P.t.esc_en_eff[ip], en_add);
-        atomicAdd(&P.t.esc_num_eff[ip], weight);
+    const bool is_cross = (fl & EV_VALID) && !(fl & EV_FINISH), is_fin = (fl & EV_VALID) && (fl & EV_FINISH);
+    const bool inj = fl & EV_INJ, up = fl & EV_UP;
+    const double g0u0w = weight * P.gam0 * P.u0;  // reference order: value * weight * gam0 * u0 (kept below)
+    (void)g0u0w;
+    double sc[SC_N];
+#pragma unroll
+    for (int k = 0; k < SC_N; k++) sc[k] = 0.0;
+    int lo = 1, hi = 0;
+    double f_pxx = 0, f_pxz = 0, f_en = 0;
+    bool thermal = false;
+
+    if (is_cross) {
+        double pt_o_px_sk, abs_inv_vx;
+        if (ptot_sk > fabs(sx * SPIKE_AWAY)) {
+            pt_o_px_sk = SPIKE_AWAY;
+            abs_inv_vx = fabs(SPIKE_AWAY / ux);
+        } else {
+            pt_o_px_sk = ptot_sk / sx;
+            abs_inv_vx = fabs(gam_sk * P.aa * P.mp / sx);
+        }
+        double en_add;
+        if ((gam_sk - 1) > P.E_rel_pt) en_add = (gam_sk - 1) * P.m * (P.c * P.c) * weight;
+        else en_add = ptot_sk * ptot_sk / (2 * P.m) * weight;
+        const uint32_t xmask = fl >> EV_XSPEC_SHIFT;
+        if (xmask) {  // calculate_x_spec_spectra! :164-190
+            double pt_o_px_pf = fmin(fabs(ptot / pb), SPIKE_AWAY);
+            int ipt = psd_bin_momentum(P, ptot_sk), ipf = psd_bin_momentum(P, ptot);
+            for (int i = 0; i < P.n_xspec; i++)
+                if (xmask & (1u << i)) {
+                    red_add_f64(&P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
+                    double F = fabs(pb / sx) * (gam_sk / gam_pf);
+                    red_add_f64(&P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
+                }
+        }
+        const double sign_fac = up ? -1.0 : 1.0;
+        if (!up) { lo = i_old + 1; hi = i_new; }
+        else { lo = i_new + 1; hi = i_old; if (inj) lo = max(lo, P.i_grid_feb + 1); }  // :223-225
+        f_pxx = sign_fac * sx * weight * P.gam0 * P.u0;
+        f_pxz = fabs(sz) * weight * P.gam0 * P.u0;
+        f_en = sign_fac * en_add * P.gam0 * P.u0;
+        if (lo <= hi) {
+            const double w = weight * abs_inv_vx;
+            if (inj) {
+                int ipt = psd_bin_momentum(P, ptot_sk), jth = psd_bin_angle(P, sx, ptot_sk);
+                const size_t stride = (size_t)(P.M + 2) * (size_t)(P.T + 2);
+                double* cell = P.t.psd + (size_t)ipt + (size_t)(P.M + 2) * (size_t)jth + stride * (size_t)(lo - 1);
+                for (int i = lo; i <= hi; i++, cell += stride) red_add_f64(cell, w);
+            } else {
+                thermal = true;
+            }
+        }
+        if (fl & EV_FEB_UP) {  // :155-158
+            sc[SC_EN_ESC_UP] = en_add * P.gam0 * P.u0;
+            sc[SC_PX_ESC_UP] = -(sx * weight * P.gam0 * P.u0);
+        }
     }
+    // thermal-crossing log (all_flux.jl:242-254): slots for the whole warp claimed with one atomic
+    {
+        const int nrec = thermal ? hi - lo + 1 : 0;
+        int incl = nrec;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total > 0) {
+            unsigned long long b0 = 0;
+            if (lane == 0) b0 = atomicAdd(&P.t.counters[CNT_LOG], (unsigned long long)total);
+            b0 = __shfl_sync(FULL, b0, 0);
+            if (nrec > 0) {
+                long long slot = (long long)b0 + (incl - nrec);
+                const double w = weight * (ptot_sk > fabs(sx * SPIKE_AWAY) ? fabs(SPIKE_AWAY / ux) : fabs(gam_sk * P.aa * P.mp / sx));
+                long long over = 0;
+                for (int k = 0; k < nrec; k++, slot++) {
+                    int i = up ? hi - k : lo + k;  // reference order: downstream ascending, upstream descending
+                    if (slot < P.t.na_cr) { P.t.tg[slot] = i; P.t.tpx[slot] = sx; P.t.tpt[slot] = ptot_sk; P.t.tw[slot] = w; }
+                    else over++;
+                }
+                if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
+            }
+        }
+    }
+    if (is_fin) {
+        const int reason = (fl >> EV_REASON_SHIFT) & 7;
+        const double E0 = P.m * (P.c * P.c);
+        if (reason == 1 || reason == 2) {
+            int ip = min(psd_bin_momentum(P, ptot_sk), MCS_PSD_MAX), jt = min(psd_bin_angle(P, sx, ptot_sk), MCS_PSD_MAX);
+            double wf;
+            if (ptot_sk > fabs(SPIKE_AWAY * sx)) wf = gam_sk * P.m * SPIKE_AWAY / ptot_sk;
+            else wf = gam_sk * (P.m / fabs(sx));
+            if (reason == 1) {
+                red_add_f64(&P.t.esc_dn[ip + E1 * jt], weight * wf);
+            } else {
+                sc[SC_ESC_FLUX] = weight;
+                red_add_f64(&P.t.esc_up[ip + E1 * jt], weight * wf);
+                bool rel = (gam_sk - 1) >= P.E_rel_pt;  // F-8
+                double Ek = rel ? (gam_sk - 1) * E0 : ptot_sk * ptot_sk / (2 * P.m);
+                double en_add = Ek * weight;
+                sc[SC_PX_ESC_FEB] = fabs(sx) * weight;
+                sc[SC_EN_ESC_FEB] = en_add;
+                red_add_f64(&P.t.esc_en_eff[ip], en_add);
+                red_add_f64(&P.t.esc_num_eff[ip], weight);
+            }
+        }
+        if (fl & EV_SUMP) {  // particle_loop.jl:478-486
+            double vel = ptot / P.m;
+            if ((gam_pf - 1) >= P.E_rel_pt) vel /= gam_pf;
+            sc[SC_SUMP] = ptot / 3 * vel * weight * P.n0;
+            sc[SC_SUMKE] = (gam_pf - 1) * P.m * (P.c * P.c) * weight * P.n0;
+        }
+    }
+    // ---- ordered accumulation into the warp's partials: events in queue order, lanes spread over the zones ----
+    unsigned todo = __ballot_sync(FULL, is_cross && lo <= hi);
+    while (todo) {
+        const int e = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int lo_e = __shfl_sync(FULL, lo, e), hi_e = __shfl_sync(FULL, hi, e);
+        const double a = __shfl_sync(FULL, f_pxx, e), b = __shfl_sync(FULL, f_pxz, e), c = __shfl_sync(FULL, f_en, e);
+        const int th = __shfl_sync(FULL, (int)thermal, e);
+        for (int j = lo_e + lane; j <= hi_e; j += 32) {
+            wm.part[j - 1] += a;
+            wm.part[ng + j - 1] += b;
+            wm.part[2 * ng + j - 1] += c;
+            if (th) reinterpret_cast<unsigned long long*>(wm.part)[3 * ng + j - 1] += 1ull;
+        }
+    }
+    bool any_sc = false;
+#pragma unroll
+    for (int k = 0; k < SC_N; k++) any_sc |= sc[k] != 0.0;
+    if (__any_sync(FULL, any_sc)) {
+#pragma unroll
+        for (int k = 0; k < SC_N - 1; k++) {
+            double v = sc[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);  // fixed butterfly order
+            if (lane == 0) wm.part[4 * ng + k] += v;
+        }
+    }
+    __syncwarp();
 }
 
-// all_flux.jl:86-158 once the zone has changed (or an x_spec / FEB detector may have been crossed).
-// sh_flux: per-block shared tallies [pxx | pxz | efl | crossings] of n_grid entries each.
-__device__ __noinline__ void flux_tallies(const DevParams& P, double* sh_flux, double pb, double pperp, double ptot,
-                                          double gam_pf, double phi, double weight, int i_grid, int i_grid_old,
-                                          double ux, double gsf, double bcos, double bsin, double x, double x_old,
-                                          bool inj) {
-    const int ng = P.n_grid;
-    double ptot_sk, sx, sz, gam_sk;
-    transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
-    double pt_o_px_sk, abs_inv_vx;
-    if (ptot_sk > fabs(sx * SPIKE_AWAY)) {
-        pt_o_px_sk = SPIKE_AWAY;
-        abs_inv_vx = fabs(SPIKE_AWAY / ux);
-    } else {
-        pt_o_px_sk = ptot_sk / sx;
-        abs_inv_vx = fabs(gam_sk * P.aa * P.mp / sx);
-    }
-    double en_add;
-    if ((gam_sk - 1) > P.E_rel_pt) en_add = (gam_sk - 1) * P.m * (P.c * P.c) * weight;
-    else en_add = ptot_sk * ptot_sk / (2 * P.m) * weight;
-
-    if (P.n_xspec > 0) {  // calculate_x_spec_spectra! :164-190
-        double pt_o_px_pf = fmin(fabs(ptot / pb), SPIKE_AWAY);
-        int ipt = psd_bin_momentum(P, ptot_sk), ipf = psd_bin_momentum(P, ptot);
-        for (int i = 0; i < P.n_xspec; i++) {
-            double xs = P.x_spec[i];
-            if ((x_old < xs && x >= xs) || (x <= xs && x_old > xs)) {
-                atomicAdd(&P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
-                double F = fabs(pb / sx) * (gam_sk / gam_pf);
-                atomicAdd(&P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
-            }
-        }
-    }
-    int lo, hi;
-    bool up = !(x > x_old);
-    double sign_fac = up ? -1.0 : 1.0;
-    if (!up) { lo = i_grid_old + 1; hi = i_grid; }
-    else { lo = i_grid + 1; hi = i_grid_old; if (inj) lo = max(lo, P.i_grid_feb + 1); }  // :223-225
-    if (lo <= hi) {
-        const double f_pxx = sign_fac * sx * weight * P.gam0 * P.u0;
-        const double f_pxz = fabs(sz) * weight * P.gam0 * P.u0;
-        const double f_en = sign_fac * en_add * P.gam0 * P.u0;
-        if (inj) {
-            int ipt = psd_bin_momentum(P, ptot_sk), jth = psd_bin_angle(P, sx, ptot_sk);
-            const size_t stride = (size_t)(P.M + 2) * (size_t)(P.T + 2);
-            double* cell = P.t.psd + (size_t)ipt + (size_t)(P.M + 2) * (size_t)jth + stride * (size_t)(lo - 1);
-            const double w = weight * abs_inv_vx;
-            for (int i = lo; i <= hi; i++, cell += stride) {
-                atomicAdd(&sh_flux[i - 1], f_pxx);
-                atomicAdd(&sh_flux[ng + i - 1], f_pxz);
-                atomicAdd(&sh_flux[2 * ng + i - 1], f_en);
-                atomicAdd(cell, w);
-            }
+// Everything of the downstream end of Code Block 2 that is not the common case: downstream_test (particle_loop.jl:595-637)
+// and prob_return (prob_return.jl:36-173).  Returns fin (-1 = keeps running).
+template <bool DEBUG, bool ELECTRON>
+__device__ __noinline__ int downstream_block(const DevParams& P, Rng& rng, double& x, double x_old, double& prp_x,
+                                             double& ptot, double& pb, double& pperp, double& gam_pf, double& gd,
+                                             double grt, double& acct, double& phi, double weight, int& tcut, int helix,
+                                             int& i_return, long long& retro_steps, bool& went_retro, bool& lose_pt) {
+    const bool custom = P.flags & F_CUSTOM_EPSB;
+    int fin = -1;
+    bool do_prob_ret = true;
+    if (P.feb_dn > 0 && x > P.feb_dn) {
+        i_return = 0; do_prob_ret = false;
+    } else if (x > 1.1 * prp_x) {
+        double v_fac;
+        if (ELECTRON && ptot < P.pe_crit) {
+            double gyro_fac = P.pe_crit * P.c * gd;
+            v_fac = gyro_fac * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
         } else {
-            // thermal particle: one log record per boundary (all_flux.jl:242-254); slots claimed in one atomic
-            const int nrec = hi - lo + 1;
-            long long base = (long long)atomicAdd(&P.t.counters[CNT_LOG], (unsigned long long)nrec);
-            const double w = weight * abs_inv_vx;
-            long long over = 0;
-            for (int k = 0; k < nrec; k++) {
-                int i = up ? hi - k : lo + k;  // reference order: downstream ascending, upstream descending
-                atomicAdd(&sh_flux[i - 1], f_pxx);
-                atomicAdd(&sh_flux[ng + i - 1], f_pxz);
-                atomicAdd(&sh_flux[2 * ng + i - 1], f_en);
-                atomicAdd((unsigned long long*)&sh_flux[3 * ng + i - 1], 1ull);
-                long long slot = base + k;
-                if (slot < P.t.na_cr) {
-                    P.t.tg[slot] = i; P.t.tpx[slot] = sx; P.t.tpt[slot] = ptot_sk; P.t.tw[slot] = w;
+            v_fac = grt * ptot / (P.m * gam_pf * P.u2);
+        }
+        double L = P.eta_mfp / 3 * v_fac;
+        if (x > 6.91 * L) { i_return = 0; do_prob_ret = false; }
+    }
+    if (do_prob_ret) {
+        i_return = 2;
+        if (x < P.x_grid_stop) {
+        } else if (x_old < P.x_grid_stop && P.x_grid_stop <= x) {
+            double gyro_tmp = (custom && x > P.x_grid_stop) ? sqrt(P.x_grid_stop / x) : 1.0;
+            double g2 = ptot * P.c * gyro_tmp / (P.qcgs * P.bmag2);  // K-5
+            double L = P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2);
+            prp_x = x + 3 * L;
+        } else if (x_old < prp_x && x >= prp_x) {
+            double vt = ptot / (gam_pf * P.aa * P.mp);
+            double r = (vt - P.u2) / (vt + P.u2);
+            if (vt < P.u2 || uniform<DEBUG>(rng, P) > r * r) {
+                i_return = 0;
+            } else {
+                i_return = 1;
+                if (!(P.flags & F_RETRO)) {
+                    fin = MCS_FATE_ERROR;  // reference: error() prob_return.jl:134
                 } else {
-                    over++;
+                    went_retro = true;
+                    lose_pt = retro_time<DEBUG, ELECTRON>(P, rng, gd, prp_x, ptot, pb, pperp, gam_pf, acct, weight, tcut,
+                                                         phi, retro_steps);
+                    if (lose_pt) i_return = 0;
+                    x = prp_x;
                 }
             }
-            if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
+        } else if (ELECTRON && ptot < P.pcut_prev && helix % 1000 == 0) {
+            double g2 = ptot * P.c * gd;
+            double L = P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2);
+            if (x > 2.0e3 * L) prp_x = 0.8 * x;
+            else prp_x = fmin(prp_x, P.x_grid_stop + L * pow(P.pcut_prev / ptot, 5.0));
         }
     }
-    if (inj && x < P.feb_up && x_old >= P.feb_up) {  // :155-158
-        atomicAdd(&P.t.scalars[SC_EN_ESC_UP], en_add * P.gam0 * P.u0);
-        atomicAdd(&P.t.scalars[SC_PX_ESC_UP], -(sx * weight * P.gam0 * P.u0));
+    return fin;
+}
+
+// no_DSA_loop reflection branch (particle_loop.jl:551-568): only when a not-yet-injected particle steps back upstream
+template <bool DEBUG>
+__device__ __noinline__ bool reflect_loop(const DevParams& P, Rng& rng, double& pb, double& phi, double& x, double x_old,
+                                          double phi_old, double dphi, double t_step, double inv_gm, double gsf,
+                                          double bcos, double bsin, double gr, double ux) {
+    for (int pass = 0;; pass++) {
+        if ((P.flags & F_DONT_DSA) || uniform<DEBUG>(rng, P) > P.inj_frac) {
+            if (pb < 0) pb = -pb; else phi = uniform<DEBUG>(rng, P) * TWO_PI;
+        } else return false;
+        phi = mod2pi(phi + dphi);
+        double x_move = pb * t_step * inv_gm;
+        double gyr = bsin != 0.0 ? gr * bsin * (cos(phi) - cos(phi_old)) : 0.0;
+        x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
+        if (!(x <= 0 && x_old > 0)) return false;
+        if (pass > 1000) return true;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // The transport kernel.
-template <bool DEBUG>
-__global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant__ DevParams P) {
-    extern __shared__ double sh_flux[];  // [4*n_grid]
+template <bool DEBUG, bool ELECTRON>
+__global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(const __grid_constant__ DevParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const int ng = P.n_grid;
-    for (int i = threadIdx.x; i < 4 * ng; i += blockDim.x) sh_flux[i] = 0.0;
-    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const WarpMem wm = warp_mem(smem, warp, ng);
+    for (int i = lane; i < 4 * ng + SC_N; i += 32) wm.part[i] = 0.0;
+    __syncwarp();
 
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const uint32_t flags = P.flags;
-    const bool custom = flags & F_CUSTOM_EPSB, dont_scatter = flags & F_DONT_SCATTER;
+    const bool custom = flags & F_CUSTOM_EPSB, dont_scatter = flags & F_DONT_SCATTER, dynamic = flags & F_DYNAMIC_QUEUE;
+    const bool rad = ELECTRON && (flags & F_RAD_LOSSES);
+    const long long total_warps = (long long)gridDim.x * n_warps, gwarp = (long long)blockIdx.x * n_warps + warp;
 
     // lane state -------------------------------------------------------------------------------
-    long long ip = -1;
+    long long ip = -1, next_j = 0;
     bool queue_empty = false;
-    double weight = 0, ptot = 0, pb = 0, pperp = 0, x = 0, x_old = 0, xn_per = 0, prp_x = 0, acct = 0, phi = 0;
-    double gam_pf = 1, gd = 0, grt = 0, gr = 0, gper = 0, t_step = 0;
+    double weight = 0, ptot = 1, pb = 0, pperp = 0, x = 0, x_old = 0, xn_per = 0, prp_x = 0, acct = 0, phi = 0;
+    double gam_pf = 1, gd = 0, grt = 0, gr = 0, gper = 0, t_step = 0, inv_ptot = 1, inv_gm = 1;
     double ux = 0, gsf = 1, gef = 1, bsin = 0, bcos = 1;
-    int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1;
+    int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1, xsel = 0;
     bool down = false, inj = false;
     long long retro_steps = 0;
     unsigned long long tot_helix = 0, tot_retro = 0;
+    int qn = 0;  // events queued by this warp (warp-uniform)
     Rng rng;
     rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
     int slot = -1;
 
     for (;;) {
-        // ---- refill idle lanes from the global queue: one atomic per warp ------------------------
+        // ---- refill idle lanes ---------------------------------------------------------------------
         unsigned need = __ballot_sync(FULL, ip < 0 && !queue_empty);
-        if (need) {
-            long long base = 0;
-            int leader = __ffs(need) - 1;
-            if (lane == leader) base = (long long)atomicAdd(&P.t.counters[CNT_QUEUE], (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
+        if (MCS_UNLIKELY(need != 0u)) {
+            const int rank = __popc(need & ((1u << lane) - 1u));
+            long long base;
+            if (dynamic) {  // one atomic per warp on the global queue head
+                base = 0;
+                const int leader = __ffs(need) - 1;
+                if (lane == leader) base = (long long)atomicAdd(&P.t.counters[CNT_QUEUE], (unsigned long long)__popc(need));
+                base = __shfl_sync(FULL, base, leader);
+            } else {  // deterministic: chunks of 32 consecutive particles dealt round-robin to the warps
+                base = next_j;
+                next_j += __popc(need);
+            }
             if (ip < 0 && !queue_empty) {
-                long long mine = base + __popc(need & ((1u << lane) - 1u));
+                long long j = base + rank;
+                long long mine = dynamic ? j : ((j >> 5) * total_warps + gwarp) * 32 + (j & 31);
                 if (mine < P.n_use) {
                     ip = mine;
                     // particle_loop.jl:44-96, 131-153
@@ -515,6 +741,7 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                     i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
                     down = P.cur.down[ip]; inj = P.cur.inj[ip];
                     helix = 0; i_return = -1; t_step = 0.0; x_old = 0.0; retro_steps = 0;
+                    xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
                     gam_pf = hypot(1.0, ptot / P.mc);
                     gd = 1 / (P.zz * P.bt[i_grid]);
                     if (custom && x > P.x_grid_stop) gd *= sqrt(x / P.x_grid_stop);
@@ -524,6 +751,7 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                     ux = P.ux[iz]; gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
                     pperp = perpendicular_momentum(P, ptot, pb);
                     gr = pperp * P.c * gd;
+                    inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
                     rng.n = 0; rng.c1 = (uint32_t)(P.first_global + ip); rng.exhausted = false;
                     if (DEBUG) {
                         rng.ru = nullptr; rng.rn = 0;
@@ -540,266 +768,289 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
         }
         if (__all_sync(FULL, ip < 0)) break;
 
+        // ---- one pass of the helix loop (particle_loop.jl:154-499) ------------------------------------
+        int fin = -1;          // -1 running; 0 saved; 1..4 i_reason; 5 error
+        uint32_t ev = 0;       // crossing event to queue at point A
+        bool moved = false;
         if (ip >= 0) {
-            // ---- one pass of the helix loop (particle_loop.jl:154-499) -----------------------------
-            int fin = -1;  // -1 running; 0 saved; 1..4 i_reason; 5 error
             helix++;
-            if (helix > P.helix_cap) {
+            if (MCS_UNLIKELY(helix > P.helix_cap)) {
                 fin = 1;  // K-1
+            } else if (MCS_UNLIKELY(i_return == 1)) {
+                pperp = perpendicular_momentum(P, ptot, pb);
+                gr = pperp * P.c * gd;
             } else {
-                if (i_return == 1) {
-                    pperp = perpendicular_momentum(P, ptot, pb);
-                    gr = pperp * P.c * gd;
-                } else {
-                    // Code Block 3
-                    const int iz_old = iz;
-                    if (i_grid != iz) {
-                        iz = i_grid;
-                        ux = P.ux[iz]; gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
-                    }
-                    double bmag = (custom && x > P.x_grid_stop) ? P.bt[ng] * sqrt(P.x_grid_stop / x) : P.bt[iz];
+                // Code Block 3
+                const int iz_old = iz;
+                const bool zc = i_grid != iz;
+                if (MCS_UNLIKELY(zc)) {
+                    iz = i_grid;
+                    ux = P.ux[iz]; gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                    gd = 1 / (P.zz * P.bt[iz]);
+                }
+                double bmag = 0.0;
+                if (custom || rad) {
+                    bmag = (custom && x > P.x_grid_stop) ? P.bt[ng] * sqrt(P.x_grid_stop / x) : P.bt[iz];
                     gd = 1 / (P.zz * bmag);
-                    if (iz != iz_old && ux != P.ux[iz_old]) {
-                        transform_p_PSP(P, iz_old, iz, ptot, pb, pperp, gam_pf, phi);
-                        gr = pperp * P.c * gd;
+                }
+                if (MCS_UNLIKELY(zc && ux != P.ux[iz_old])) {
+                    transform_p_PSP(P, iz_old, iz, ptot, pb, pperp, gam_pf, phi);
+                    gr = pperp * P.c * gd;
+                    grt = ptot * P.c * gd;
+                    inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
+                }
+                if (MCS_UNLIKELY(P.energy_transfer_frac > 0 && !inj && x_old <= 0 && i_grid_old != i_grid)) {
+                    do_energy_transfer(P, i_grid, i_grid_old, ptot, pb, pperp, gam_pf, weight);
+                    inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
+                }
+                if (dont_scatter && x > 10 * gr) {
+                    i_return = 0; fin = 1;
+                } else if (MCS_UNLIKELY(ptot > P.pmax_cutoff) && above_pmax_shock_frame(P, pb, pperp, gam_pf, phi, iz)) {
+                    fin = 2;
+                }
+                if (MCS_UNLIKELY(fin < 0 && inj && x < P.feb_up)) fin = 2;
+                if (MCS_UNLIKELY(fin < 0 && P.age_max > 0 && acct > P.age_max)) fin = 3;
+                if (rad && fin < 0) {
+                    double p_old = ptot, Bcmb = P.B_CMBz * gef;
+                    ptot = radiation_loss(P, bmag * bmag + Bcmb * Bcmb, ptot, t_step);
+                    if (ptot <= 0) {
+                        ptot = 1.0e-99; pb = 1.0e-99; pperp = 1.0e-99; gam_pf = 1;
+                        fin = 4;
+                    } else {
+                        gam_pf = hypot(ptot / P.mc, 1.0);
+                        pb *= ptot / p_old;
+                        pperp *= ptot / p_old;
                         grt = ptot * P.c * gd;
+                        gr = pperp * P.c * gd;
+                        inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
                     }
-                    if (P.energy_transfer_frac > 0 && !inj && x_old <= 0 && i_grid_old != i_grid)
-                        do_energy_transfer(P, i_grid, i_grid_old, ptot, pb, pperp, gam_pf, weight);
-                    if (dont_scatter && x > 10 * gr) {
-                        i_return = 0; fin = 1;
-                    } else if (ptot > P.pmax_cutoff) {
-                        double ptot_sk, sx, sz, gam_sk;
-                        transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
-                        if (ptot_sk > P.pmax_cutoff) fin = 2;
-                    }
-                    if (fin < 0 && inj && x < P.feb_up) fin = 2;
-                    if (fin < 0 && P.age_max > 0 && acct > P.age_max) fin = 3;
-                    if (fin < 0 && (flags & F_RAD_LOSSES) && P.aa < 1) {
-                        double p_old = ptot, Bcmb = P.B_CMBz * gef;
-                        ptot = radiation_loss(P, bmag * bmag + Bcmb * Bcmb, ptot, t_step);
-                        if (ptot <= 0) {
-                            ptot = 1.0e-99; pb = 1.0e-99; pperp = 1.0e-99; gam_pf = 1;
-                            fin = 4;
-                        } else {
-                            gam_pf = hypot(ptot / P.mc, 1.0);
-                            pb *= ptot / p_old;
-                            pperp *= ptot / p_old;
-                            grt = ptot * P.c * gd;
-                            gr = pperp * P.c * gd;
+                }
+                if (MCS_LIKELY(fin < 0)) {
+                    if (MCS_LIKELY(!dont_scatter)) {
+                        // scattering.jl:29-101; cos_max depends on xn_per only and is precomputed
+                        if (ELECTRON && ptot < P.pe_crit) gper = TWO_PI * P.gam_e_crit * P.mc * gd;
+                        else gper = TWO_PI * gam_pf * P.mc * gd;
+                        double omc;
+                        if (xsel < 2) omc = P.omc[xsel];
+                        else omc = 1 - cos(sqrt(6 * TWO_PI / (xn_per * P.eta_mfp)));
+                        double u1, u2;
+                        uniform2<DEBUG>(rng, P, u1, u2);
+                        const double cos_old = pb * inv_ptot, sin_old = pperp * inv_ptot;
+                        const double cos_d = 1 - u1 * omc;
+                        const double sin_d = sqrt_guard(P, 1 - cos_d * cos_d);
+                        const double phi_s = u2 * TWO_PI - PI;
+                        double sps, cps;
+                        sincos_bf(phi_s, &sps, &cps);
+                        const double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
+                        const double sin_new = sqrt_guard(P, 1 - cos_new * cos_new);
+                        pb = ptot * cos_new;
+                        pperp = ptot * sin_new;
+                        double phi_p = phi + HALF_PI;
+                        if (MCS_LIKELY(sin_new != 0)) {
+                            double s = sps * sin_d / sin_new;
+                            if (fabs(s) > SIN_UPPER_LIMIT) s = copysign(SIN_UPPER_LIMIT, s);
+                            phi_p += asin_bf(s);
                         }
+                        phi = phi_p - HALF_PI;
+                    }
+                    if (down) {
+                        acct += t_step * gef;
+                        if (MCS_UNLIKELY((flags & F_TCUTS) && tcut <= P.n_tcuts && acct >= P.tcuts[tcut - 1])) {
+                            tcut_track(P, tcut, weight, ptot);
+                            tcut++;
+                        }
+                        if (MCS_UNLIKELY(ptot > P.pcut)) fin = 0;  // saved below
                     }
                     if (fin < 0) {
-                        if (!dont_scatter) {
-                            // scattering.jl:29-101
-                            double grt_s;
-                            if (P.aa < 1 && ptot < P.pe_crit) {
-                                grt_s = P.pe_crit * P.c * gd;
-                                gper = TWO_PI * P.gam_e_crit * P.mc * gd;
-                            } else {
-                                grt_s = ptot * P.c * gd;
-                                gper = TWO_PI * gam_pf * P.mc * gd;
-                            }
-                            double vp_tg = TWO_PI * grt_s, lambda = P.eta_mfp * grt_s;
-                            double cos_max = cos(sqrt(6 * vp_tg / (xn_per * lambda)));
-                            double cos_old = pb / ptot, sin_old = pperp / ptot;
-                            double cos_d = 1 - uniform<DEBUG>(rng, P) * (1 - cos_max);
-                            double sin_d = sqrt_guard(P, 1 - cos_d * cos_d);
-                            double phi_s = uniform<DEBUG>(rng, P) * TWO_PI - PI;
-                            double sps, cps;
-                            sincos(phi_s, &sps, &cps);
-                            double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
-                            double sin_new = sqrt_guard(P, 1 - cos_new * cos_new);
-                            pb = ptot * cos_new;
-                            pperp = ptot * sin_new;
-                            double phi_p = phi + HALF_PI;
-                            if (sin_new != 0) {
-                                double s = sps * sin_d / sin_new;
-                                if (fabs(s) > SIN_UPPER_LIMIT) s = copysign(SIN_UPPER_LIMIT, s);
-                                phi_p += asin(s);
-                            }
-                            phi = phi_p - HALF_PI;
-                        }
-                        if (down) {
-                            acct += t_step * gef;
-                            if ((flags & F_TCUTS) && tcut <= P.n_tcuts && acct >= P.tcuts[tcut - 1]) {
-                                tcut_track(P, tcut, weight, ptot);
-                                tcut++;
-                            }
-                            if (ptot > P.pcut) fin = 0;  // saved below
-                        }
-                        if (fin < 0) xn_per = x > grt ? P.xn_coarse : P.xn_fine;
-                    }
-                }
-                if (fin < 0) {
-                    // Code Block 2
-                    x_old = x;
-                    const double phi_old = phi;
-                    t_step = gper / xn_per;
-                    bool err = false;
-                    for (int pass = 0;; pass++) {  // no_DSA_loop :510-571
-                        phi = mod2pi(phi + TWO_PI / xn_per);
-                        double x_move = pb * t_step / (gam_pf * P.m);
-                        double gyr = bsin != 0.0 ? gr * bsin * (cos(phi) - cos(phi_old)) : 0.0;
-                        x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
-                        if (x <= 0 && x_old > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)) {
-                            if ((flags & F_DONT_DSA) || uniform<DEBUG>(rng, P) > P.inj_frac) {
-                                if (pb < 0) pb = -pb; else phi = uniform<DEBUG>(rng, P) * TWO_PI;
-                            } else break;
-                        } else break;
-                        if (pass > 1000) { err = true; break; }
-                    }
-                    if (x_old < 0 && x >= 0) {
-                        down = true;
-                        double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
-                        prp_x = fmax(prp_x, L);
-                    }
-                    if (down && x < 0) inj = true;
-
-                    // all_flux.jl:65-82: linear scans from the current zone (K-3)
-                    i_grid_old = i_grid;
-                    if (x > x_old) {
-                        int k = i_grid + 1;
-                        while (k <= ng + 1 && !(P.xg[k] > x)) k++;
-                        if (k > ng + 1) err = true;
-                        i_grid = k - 1;
-                    } else {
-                        int k = i_grid;
-                        while (k >= 0 && !(P.xg[k] <= x)) k--;
-                        if (k < 0) err = true;
-                        i_grid = k;
-                    }
-                    if (err) {
-                        fin = MCS_FATE_ERROR;
-                        i_grid = i_grid_old;
-                    } else {
-                        if (!(i_grid == i_grid_old && i_grid > P.i_grid_feb && P.n_xspec == 0))
-                            flux_tallies(P, sh_flux, pb, pperp, ptot, gam_pf, phi, weight, i_grid, i_grid_old, ux, gsf,
-                                         bcos, bsin, x, x_old, inj);
-                        // downstream_test :595-637
-                        bool do_prob_ret = true, went_retro = false, lose_pt = false;
-                        if (P.feb_dn > 0 && x > P.feb_dn) {
-                            i_return = 0; do_prob_ret = false;
-                        } else if (x > 1.1 * prp_x) {
-                            double v_fac;
-                            if (P.aa < 1 && ptot < P.pe_crit) {
-                                double gyro_fac = P.pe_crit * P.c * gd;
-                                v_fac = gyro_fac * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
-                            } else {
-                                v_fac = grt * ptot / (P.m * gam_pf * P.u2);
-                            }
-                            double L = P.eta_mfp / 3 * v_fac;
-                            if (x > 6.91 * L) { i_return = 0; do_prob_ret = false; }
-                        }
-                        if (do_prob_ret) {
-                            // prob_return.jl:36-173
-                            i_return = 2;
-                            if (x < P.x_grid_stop) {
-                            } else if (x_old < P.x_grid_stop && P.x_grid_stop <= x) {
-                                double gyro_tmp = (custom && x > P.x_grid_stop) ? sqrt(P.x_grid_stop / x) : 1.0;
-                                double g2 = ptot * P.c * gyro_tmp / (P.qcgs * P.bmag2);  // K-5
-                                double L = P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2);
-                                prp_x = x + 3 * L;
-                            } else if (x_old < prp_x && x >= prp_x) {
-                                double vt = ptot / (gam_pf * P.aa * P.mp);
-                                double r = (vt - P.u2) / (vt + P.u2);
-                                if (vt < P.u2 || uniform<DEBUG>(rng, P) > r * r) {
-                                    i_return = 0;
-                                } else {
-                                    i_return = 1;
-                                    if (!(flags & F_RETRO)) {
-                                        fin = MCS_FATE_ERROR;  // reference: error() prob_return.jl:134
-                                    } else {
-                                        went_retro = true;
-                                        lose_pt = retro_time<DEBUG>(P, rng, gd, prp_x, ptot, pb, pperp, gam_pf, acct,
-                                                                    weight, tcut, phi, retro_steps);
-                                        if (lose_pt) i_return = 0;
-                                        x = prp_x;
-                                    }
-                                }
-                            } else if (P.aa < 1 && ptot < P.pcut_prev && helix % 1000 == 0) {
-                                double g2 = ptot * P.c * gd;
-                                double L = P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2);
-                                if (x > 2.0e3 * L) prp_x = 0.8 * x;
-                                else prp_x = fmin(prp_x, P.x_grid_stop + L * pow(P.pcut_prev / ptot, 5.0));
-                            }
-                        }
-                        if (DEBUG && slot >= 0) {
-                            int k = P.trace_cnt[slot];
-                            if (k < P.trace_max) {
-                                McsTraceRec& r = P.trace_recs[(size_t)slot * P.trace_max + k];
-                                r.x_cm = x; r.ptot_pf = ptot; r.pb_pf = pb; r.phi_rad = phi; r.acctime_sec = acct;
-                                r.prp_x_cm = prp_x; r.i_grid = i_grid; r.helix_count = helix;
-                                r.flags = (down ? 1 : 0) | (inj ? 2 : 0) | (went_retro ? 4 : 0) | ((i_return + 1) << 8);
-                                r.n_draws = (int)rng.n;
-                                P.trace_cnt[slot] = k + 1;
-                            }
-                        }
-                        if (fin < 0 && i_return == 0) {
-                            double vel = ptot / P.m;
-                            if ((gam_pf - 1) >= P.E_rel_pt) vel /= gam_pf;
-                            atomicAdd(&P.t.scalars[SC_SUMP], ptot / 3 * vel * weight * P.n0);
-                            atomicAdd(&P.t.scalars[SC_SUMKE], (gam_pf - 1) * P.m * (P.c * P.c) * weight * P.n0);
-                            fin = lose_pt ? 4 : 1;
-                        }
-                        if (DEBUG && fin < 0 && rng.exhausted) fin = MCS_FATE_ERROR;
+                        const bool coarse = x > grt;
+                        xn_per = coarse ? P.xn_coarse : P.xn_fine;
+                        xsel = coarse ? 1 : 0;
                     }
                 }
             }
-            // ---- the particle left the loop --------------------------------------------------------
-            if (fin >= 0) {
-                if (DEBUG && rng.exhausted) fin = MCS_FATE_ERROR;
-                if (fin == 0) {  // particle_loop.jl:361-380
-                    P.l_save[ip] = 1;
-                    P.saved.weight[ip] = weight; P.saved.ptot[ip] = ptot; P.saved.pb[ip] = pb; P.saved.x[ip] = x;
-                    P.saved.grid[ip] = i_grid; P.saved.down[ip] = down; P.saved.inj[ip] = inj;
-                    P.saved.xn_per[ip] = xn_per; P.saved.prp_x[ip] = x < prp_x ? prp_x : x * 1.1;
-                    P.saved.acctime[ip] = acct; P.saved.phi[ip] = phi; P.saved.tcut[ip] = tcut;
-                } else if (fin <= 4) {
-                    particle_finish(P, fin, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, weight);
-                } else {
-                    count(P, CNT_ERR);
+            if (MCS_LIKELY(fin < 0)) {
+                // Code Block 2: move (no_DSA_loop :510-571), shock crossing, zone search (all_flux.jl:65-82)
+                moved = true;
+                x_old = x;
+                const double phi_old = phi;
+                double dphi;
+                if (xsel < 2) { t_step = gper * P.inv_xn[xsel]; dphi = P.dphi[xsel]; }
+                else { t_step = gper / xn_per; dphi = TWO_PI / xn_per; }
+                phi = mod2pi(phi + dphi);
+                const double x_move = pb * t_step * inv_gm;
+                const double gyr = MCS_UNLIKELY(bsin != 0.0) ? gr * bsin * (cos_bf(phi) - cos_bf(phi_old)) : 0.0;
+                x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
+                bool err = false;
+                if (MCS_UNLIKELY(x <= 0 && x_old > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)))
+                    err = reflect_loop<DEBUG>(P, rng, pb, phi, x, x_old, phi_old, dphi, t_step, inv_gm, gsf, bcos, bsin, gr, ux);
+                if (MCS_UNLIKELY(x_old < 0 && x >= 0)) {
+                    down = true;
+                    double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
+                    prp_x = fmax(prp_x, L);
                 }
-                P.fate[ip] = fin; P.helix[ip] = helix; P.retro[ip] = retro_steps; P.draws[ip] = rng.n;
-                count(P, CNT_FATE0 + fin);
-                tot_helix += (unsigned long long)helix;
-                tot_retro += (unsigned long long)retro_steps;
-                ip = -1;
+                if (down && x < 0) inj = true;
+                i_grid_old = i_grid;
+                {   // all_flux.jl:65-82. Common case first: one load decides "same zone" for either direction
+                    const bool dn = x > x_old;
+                    const double edge = P.xg[i_grid + (dn ? 1 : 0)];
+                    const bool same = dn ? (edge > x) : (edge <= x);
+                    if (MCS_UNLIKELY(!same)) {  // linear scans from the current zone (K-3)
+                        if (dn) {
+                            int k = i_grid + 1;
+                            while (k <= ng + 1 && !(P.xg[k] > x)) k++;
+                            if (k > ng + 1) err = true;
+                            i_grid = k - 1;
+                        } else {
+                            int k = i_grid;
+                            while (k >= 0 && !(P.xg[k] <= x)) k--;
+                            if (k < 0) err = true;
+                            i_grid = k;
+                        }
+                    }
+                }
+                if (MCS_UNLIKELY(err)) {
+                    fin = MCS_FATE_ERROR;
+                    i_grid = i_grid_old;
+                }
             }
         }
+        // crossing event? (all_flux.jl:80-82 early-out inverted), evaluated by every lane in converged code
+        if (moved && fin < 0 && !(i_grid == i_grid_old && i_grid > P.i_grid_feb && P.n_xspec == 0)) {
+            ev = EV_VALID | (inj ? EV_INJ : 0u) | (x > x_old ? 0u : EV_UP) |
+                 ((inj && x < P.feb_up && x_old >= P.feb_up) ? EV_FEB_UP : 0u);
+            for (int i = 0; i < P.n_xspec; i++) {
+                const double xs = P.x_spec[i];
+                if ((x_old < xs && x >= xs) || (x <= xs && x_old > xs)) ev |= 1u << (EV_XSPEC_SHIFT + i);
+            }
+        }
+        // ---- point A (converged): queue the crossing events with the state as it is right after the move ----
+        {
+            const unsigned m = __ballot_sync(FULL, ev != 0u);
+            if (m) {
+                if (ev) {
+                    const int q = qn + __popc(m & ((1u << lane) - 1u));
+                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = weight;
+                    wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
+                }
+                qn += __popc(m);
+            }
+        }
+        if (qn >= 32) {
+            __syncwarp();
+            process_events(P, wm, qn - 32, 32);
+            qn -= 32;
+        }
+        // ---- rest of Code Block 2: downstream escape / return ------------------------------------------------
+        bool sum_p = false;
+        if (moved && fin < 0) {
+            bool went_retro = false, lose_pt = false;
+            // downstream_test / prob_return do something only if the particle is beyond a downstream FEB, far beyond
+            // the PRP, has just crossed the end of the grid or the PRP, or is a cooling electron (prob_return.jl:155)
+            const bool special = (P.feb_dn > 0 && x > P.feb_dn) || (x > 1.1 * prp_x) ||
+                                 (x >= P.x_grid_stop && (x_old < P.x_grid_stop || (x_old < prp_x && x >= prp_x) || ELECTRON));
+            if (MCS_LIKELY(!special)) {
+                i_return = 2;
+            } else {
+                fin = downstream_block<DEBUG, ELECTRON>(P, rng, x, x_old, prp_x, ptot, pb, pperp, gam_pf, gd, grt, acct, phi,
+                                                        weight, tcut, helix, i_return, retro_steps, went_retro, lose_pt);
+                if (went_retro && ELECTRON) { inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m); }
+            }
+            if (DEBUG && slot >= 0 && fin < 0) {
+                int k = P.trace_cnt[slot];
+                if (k < P.trace_max) {
+                    McsTraceRec& r = P.trace_recs[(size_t)slot * P.trace_max + k];
+                    r.x_cm = x; r.ptot_pf = ptot; r.pb_pf = pb; r.phi_rad = phi; r.acctime_sec = acct;
+                    r.prp_x_cm = prp_x; r.i_grid = i_grid; r.helix_count = helix;
+                    r.flags = (down ? 1 : 0) | (inj ? 2 : 0) | (went_retro ? 4 : 0) | ((i_return + 1) << 8);
+                    r.n_draws = (int)rng.n;
+                    P.trace_cnt[slot] = k + 1;
+                }
+            }
+            if (fin < 0 && i_return == 0) { sum_p = true; fin = lose_pt ? 4 : 1; }
+            if (DEBUG && fin < 0 && rng.exhausted) fin = MCS_FATE_ERROR;
+        }
+        // ---- point B (converged): particles that left the loop ------------------------------------------------
+        ev = 0;
+        if (MCS_UNLIKELY(ip >= 0 && fin >= 0)) {
+            if (DEBUG && rng.exhausted) { fin = MCS_FATE_ERROR; sum_p = false; }
+            if (fin == 0) {  // particle_loop.jl:361-380
+                P.l_save[ip] = 1;
+                P.saved.weight[ip] = weight; P.saved.ptot[ip] = ptot; P.saved.pb[ip] = pb; P.saved.x[ip] = x;
+                P.saved.grid[ip] = i_grid; P.saved.down[ip] = down; P.saved.inj[ip] = inj;
+                P.saved.xn_per[ip] = xn_per; P.saved.prp_x[ip] = x < prp_x ? prp_x : x * 1.1;
+                P.saved.acctime[ip] = acct; P.saved.phi[ip] = phi; P.saved.tcut[ip] = tcut;
+            } else if (fin <= 4) {
+                ev = EV_VALID | EV_FINISH | ((uint32_t)fin << EV_REASON_SHIFT) | (sum_p ? EV_SUMP : 0u);
+            } else {
+                count(P, CNT_ERR);
+            }
+            P.fate[ip] = fin; P.helix[ip] = helix; P.retro[ip] = retro_steps; P.draws[ip] = rng.n;
+            count(P, CNT_FATE0 + fin);
+            tot_helix += (unsigned long long)helix;
+            tot_retro += (unsigned long long)retro_steps;
+            ip = -1;
+        }
+        {
+            const unsigned m = __ballot_sync(FULL, ev != 0u);
+            if (m) {
+                if (ev) {
+                    const int q = qn + __popc(m & ((1u << lane) - 1u));
+                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = weight;
+                    wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
+                }
+                qn += __popc(m);
+            }
+        }
+        if (qn >= 32) {  // drain a full batch (sums commute; the order is fixed by the lock-step schedule)
+            __syncwarp();
+            process_events(P, wm, qn - 32, 32);
+            qn -= 32;
+        }
     }
+    __syncwarp();
+    if (qn > 0) process_events(P, wm, 0, qn);
 
     // ---- warp totals, block partials ----------------------------------------------------------------
-    unsigned long long n_saved_dummy = 0;
-    (void)n_saved_dummy;
     for (int o = 16; o > 0; o >>= 1) {
         tot_helix += __shfl_xor_sync(FULL, tot_helix, o);
         tot_retro += __shfl_xor_sync(FULL, tot_retro, o);
     }
     if (lane == 0) {
-        if (tot_helix) atomicAdd(&P.t.counters[CNT_HELIX], tot_helix);
-        if (tot_retro) atomicAdd(&P.t.counters[CNT_RETRO], tot_retro);
+        if (tot_helix) count(P, CNT_HELIX, tot_helix);
+        if (tot_retro) count(P, CNT_RETRO, tot_retro);
     }
     __syncthreads();
-    double* part = P.t.block_partials + (size_t)blockIdx.x * (size_t)(4 * ng);
-    for (int i = threadIdx.x; i < 4 * ng; i += blockDim.x) part[i] = sh_flux[i];
+    const int np = 4 * ng + SC_N;
+    double* part = P.t.block_partials + (size_t)blockIdx.x * (size_t)np;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        if (i >= 3 * ng && i < 4 * ng) {  // crossing counts: integers
+            unsigned long long s = 0;
+            for (int w = 0; w < n_warps; w++) s += reinterpret_cast<unsigned long long*>(warp_mem(smem, w, ng).part)[i];
+            reinterpret_cast<unsigned long long*>(part)[i] = s;
+        } else {
+            double s = 0.0;
+            for (int w = 0; w < n_warps; w++) s += warp_mem(smem, w, ng).part[i];  // fixed warp order
+            part[i] = s;
+        }
+    }
 }
 
-// Sum the per-block partials in block order (run-to-run deterministic across blocks) into the ion totals.
+// Sum the per-block partials in block order (run-to-run deterministic) into the ion totals.
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int ng, double* pxx,
-                                       double* pxz, double* efl, unsigned long long* ncross) {
+                                       double* pxz, double* efl, unsigned long long* ncross, double* scalars) {
+    const int np = 4 * ng + SC_N;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 4 * ng) return;
-    if (i < 3 * ng) {
-        double s = 0.0;
-        for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * (4 * ng) + i];
-        double* dst = i < ng ? pxx + i : (i < 2 * ng ? pxz + (i - ng) : efl + (i - 2 * ng));
-        *dst += s;
-    } else {
+    if (i >= np) return;
+    if (i >= 3 * ng && i < 4 * ng) {
         unsigned long long s = 0;
         const unsigned long long* pu = reinterpret_cast<const unsigned long long*>(partials);
-        for (int b = 0; b < n_blocks; b++) s += pu[(size_t)b * (4 * ng) + i];
+        for (int b = 0; b < n_blocks; b++) s += pu[(size_t)b * np + i];
         ncross[i - 3 * ng] += s;
+    } else {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * np + i];
+        double* dst = i < ng ? pxx + i : (i < 2 * ng ? pxz + (i - ng) : (i < 3 * ng ? efl + (i - 2 * ng) : scalars + (i - 4 * ng)));
+        *dst += s;
     }
 }
 
@@ -898,7 +1149,7 @@ __global__ void atomic_peak_kernel(double* cells, long long n_cells, int iters) 
     for (int i = 0; i < iters; i++) {
         s = s * 1664525u + 1013904223u;
         long long idx = (long long)(((unsigned long long)s * (unsigned long long)n_cells) >> 32);
-        atomicAdd(&cells[idx], 1.0);
+        red_add_f64(&cells[idx], 1.0);
     }
 }
 

@@ -12,7 +12,9 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libmcs_b200.so")
+    """In-tree CUDA library. MCS_LIB may point at another build of the SAME sources (tuning variants from
+    `make -C csrc variants`); it is never a CPU library: load_cuda_library() checks the backend string."""
+    return os.environ.get("MCS_LIB") or os.path.join(_HERE, "libmcs_b200.so")
 
 
 def build(verbose: bool = False) -> str:
