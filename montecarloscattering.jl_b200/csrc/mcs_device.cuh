@@ -299,9 +299,21 @@ __device__ __noinline__ bool above_pmax_shock_frame(const DevParams& P, double p
     return ptot_sk > P.pmax_cutoff;
 }
 
+// Scratch records for the out-of-line (cold) functions.  They are passed and returned BY VALUE so that the lane's
+// long-lived state is never address-taken: a reference parameter of a noinline function pins the variable in
+// local memory for its whole lifetime (seen as LDL/STL in the hot loop of the v4 profile).
+struct Mom { double ptot, pb, pperp, gam_pf, phi; };
+struct ColdIO {
+    double x, prp_x, ptot, pb, pperp, gam_pf, gd, acct, phi;
+    long long retro_steps;
+    uint32_t rng_n, rng_s2, rng_s3;
+    int tcut, i_return, fin;
+    bool went_retro, lose_pt, exhausted, err;
+};
+
 // transformers.jl:523-607; zone `io` -> shock frame -> zone `in`
-__device__ __noinline__ void transform_p_PSP(const DevParams& P, int io, int in, double& ptot, double& pb,
-                                             double& pperp, double& gam_pf, double& phi) {
+__device__ __noinline__ Mom transform_p_PSP(const DevParams& P, int io, int in, Mom mi) {
+    double pb = mi.pb, pperp = mi.pperp, gam_pf = mi.gam_pf, phi = mi.phi;
     double ux_o = P.ux[io], uz_o = P.uz[io], ut_o = P.ut[io], gsf_o = P.gsf[io], bcos_o = P.costh[io],
            bsin_o = P.sinth[io];
     double ux = P.ux[in], uz = P.uz[in], ut = P.ut[in], gsf = P.gsf[in], bcos = P.costh[in], bsin = P.sinth[in];
@@ -332,9 +344,11 @@ __device__ __noinline__ void transform_p_PSP(const DevParams& P, int io, int in,
     } else {
         pp = sqrt(pt * pt - b * b);
     }
-    ptot = pt; pb = b; pperp = pp;
-    gam_pf = hypot(pt / P.mc, 1.0);
-    phi = atan2(ny, -nx * bsin + nz * bcos) - HALF_PI;
+    Mom mo;
+    mo.ptot = pt; mo.pb = b; mo.pperp = pp;
+    mo.gam_pf = hypot(pt / P.mc, 1.0);
+    mo.phi = atan2(ny, -nx * bsin + nz * bcos) - HALF_PI;
+    return mo;
 }
 
 __device__ __forceinline__ double perpendicular_momentum(const DevParams& P, double ptot, double pb) {
@@ -355,8 +369,8 @@ __device__ __noinline__ void tcut_track(const DevParams& P, int tcut_curr, doubl
 }
 
 // particle_loop.jl:652-723
-__device__ __noinline__ void do_energy_transfer(const DevParams& P, int i_grid, int i_grid_old, double& ptot,
-                                                double& pb, double& pperp, double& gam_pf, double weight) {
+__device__ __noinline__ Mom do_energy_transfer(const DevParams& P, int i_grid, int i_grid_old, Mom mi, double weight) {
+    double ptot = mi.ptot, pb = mi.pb, pperp = mi.pperp, gam_pf = mi.gam_pf;
     int i_start = i_grid_old, i_stop = min(i_grid, P.i_shock);
     double E0 = P.m * (P.c * P.c), gam_f = 0.0;
     bool scale = false;
@@ -387,11 +401,14 @@ __device__ __noinline__ void do_energy_transfer(const DevParams& P, int i_grid, 
         double s = pf / ptot;
         pb *= s; pperp *= s; ptot = pf; gam_pf = gam_f;
     }
+    Mom mo;
+    mo.ptot = ptot; mo.pb = pb; mo.pperp = pperp; mo.gam_pf = gam_pf; mo.phi = mi.phi;
+    return mo;
 }
 
 // prob_return.jl:217-344.  Nested loop on the lane: retro passes are ~1e-3 of all passes.
 template <bool DEBUG, bool ELECTRON>
-__device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd, double prp_x, double& ptot,
+__device__ __forceinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd, double prp_x, double& ptot,
                                         double& pb, double& pperp, double& gam_pf, double& acct, double weight,
                                         int& tcut_curr, double& phi_out, long long& n_steps) {
     const int ng = P.n_grid;
@@ -457,7 +474,7 @@ __device__ __noinline__ bool retro_time(const DevParams& P, Rng& rng, double& gd
 //                     upstream-FEB scalars);
 //   finish event   -> particle_finish.jl:46-107 and the downstream sums of particle_loop.jl:478-495.
 // The n_grid-sized tallies and the scalars go to this warp's shared partials with plain adds in event order.
-__device__ __noinline__ void process_events(const DevParams& P, const WarpMem& wm, int base, int n_ev) {
+__device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int base, int n_ev) {
     const int lane = threadIdx.x & 31, ng = P.n_grid;
     const bool act = lane < n_ev;
     const int q = base + (act ? lane : 0);
@@ -609,14 +626,19 @@ __device__ __noinline__ void process_events(const DevParams& P, const WarpMem& w
 }
 
 // Everything of the downstream end of Code Block 2 that is not the common case: downstream_test (particle_loop.jl:595-637)
-// and prob_return (prob_return.jl:36-173).  Returns fin (-1 = keeps running).
+// and prob_return (prob_return.jl:36-173) with retro_time.  State goes in and out by value (ColdIO).
 template <bool DEBUG, bool ELECTRON>
-__device__ __noinline__ int downstream_block(const DevParams& P, Rng& rng, double& x, double x_old, double& prp_x,
-                                             double& ptot, double& pb, double& pperp, double& gam_pf, double& gd,
-                                             double grt, double& acct, double& phi, double weight, int& tcut, int helix,
-                                             int& i_return, long long& retro_steps, bool& went_retro, bool& lose_pt) {
+__device__ __noinline__ ColdIO downstream_block(const DevParams& P, ColdIO io, double x_old, double grt, double weight,
+                                                int helix, uint32_t rng_c1, const double* ru, long long rn) {
     const bool custom = P.flags & F_CUSTOM_EPSB;
-    int fin = -1;
+    Rng rng;
+    rng.n = io.rng_n; rng.s2 = io.rng_s2; rng.s3 = io.rng_s3; rng.c1 = rng_c1; rng.ru = ru; rng.rn = rn;
+    rng.exhausted = io.exhausted;
+    double x = io.x, prp_x = io.prp_x, ptot = io.ptot, pb = io.pb, pperp = io.pperp, gam_pf = io.gam_pf, gd = io.gd,
+           acct = io.acct, phi = io.phi;
+    int tcut = io.tcut, i_return = io.i_return, fin = -1;
+    long long retro_steps = io.retro_steps;
+    bool went_retro = false, lose_pt = false;
     bool do_prob_ret = true;
     if (P.feb_dn > 0 && x > P.feb_dn) {
         i_return = 0; do_prob_ret = false;
@@ -663,25 +685,39 @@ __device__ __noinline__ int downstream_block(const DevParams& P, Rng& rng, doubl
             else prp_x = fmin(prp_x, P.x_grid_stop + L * pow(P.pcut_prev / ptot, 5.0));
         }
     }
-    return fin;
+    ColdIO o;
+    o.x = x; o.prp_x = prp_x; o.ptot = ptot; o.pb = pb; o.pperp = pperp; o.gam_pf = gam_pf; o.gd = gd; o.acct = acct;
+    o.phi = phi; o.retro_steps = retro_steps; o.rng_n = rng.n; o.rng_s2 = rng.s2; o.rng_s3 = rng.s3; o.tcut = tcut;
+    o.i_return = i_return; o.fin = fin; o.went_retro = went_retro; o.lose_pt = lose_pt; o.exhausted = rng.exhausted;
+    o.err = false;
+    return o;
 }
 
-// no_DSA_loop reflection branch (particle_loop.jl:551-568): only when a not-yet-injected particle steps back upstream
+// no_DSA_loop reflection branch (particle_loop.jl:551-568): only when a not-yet-injected particle steps back upstream.
+// Uses io.{x, pb, phi, rng_*}; sets io.err if the loop does not terminate.
 template <bool DEBUG>
-__device__ __noinline__ bool reflect_loop(const DevParams& P, Rng& rng, double& pb, double& phi, double& x, double x_old,
-                                          double phi_old, double dphi, double t_step, double inv_gm, double gsf,
-                                          double bcos, double bsin, double gr, double ux) {
+__device__ __noinline__ ColdIO reflect_loop(const DevParams& P, ColdIO io, double x_old, double phi_old, double dphi,
+                                            double t_step, double inv_gm, double gsf, double bcos, double bsin, double gr,
+                                            double ux, uint32_t rng_c1, const double* ru, long long rn) {
+    Rng rng;
+    rng.n = io.rng_n; rng.s2 = io.rng_s2; rng.s3 = io.rng_s3; rng.c1 = rng_c1; rng.ru = ru; rng.rn = rn;
+    rng.exhausted = io.exhausted;
+    double pb = io.pb, phi = io.phi, x = io.x;
+    bool err = false;
     for (int pass = 0;; pass++) {
         if ((P.flags & F_DONT_DSA) || uniform<DEBUG>(rng, P) > P.inj_frac) {
             if (pb < 0) pb = -pb; else phi = uniform<DEBUG>(rng, P) * TWO_PI;
-        } else return false;
+        } else break;
         phi = mod2pi(phi + dphi);
         double x_move = pb * t_step * inv_gm;
         double gyr = bsin != 0.0 ? gr * bsin * (cos(phi) - cos(phi_old)) : 0.0;
         x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
-        if (!(x <= 0 && x_old > 0)) return false;
-        if (pass > 1000) return true;
+        if (!(x <= 0 && x_old > 0)) break;
+        if (pass > 1000) { err = true; break; }
     }
+    io.pb = pb; io.phi = phi; io.x = x; io.err = err;
+    io.rng_n = rng.n; io.rng_s2 = rng.s2; io.rng_s3 = rng.s3; io.exhausted = rng.exhausted;
+    return io;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -701,17 +737,18 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     const long long total_warps = (long long)gridDim.x * n_warps, gwarp = (long long)blockIdx.x * n_warps + warp;
 
     // lane state -------------------------------------------------------------------------------
-    long long ip = -1, next_j = 0;
+    // Kept small on purpose (128-register budget at 16 warps/SM): weight and a non-standard xn_per are re-read from
+    // the population arrays where needed, retro_time pass counts accumulate in P.retro[ip], x_old survives a pass only
+    // as the one bit Code Block 3 needs.
+    int ip = -1, next_j = 0;
     bool queue_empty = false;
-    double weight = 0, ptot = 1, pb = 0, pperp = 0, x = 0, x_old = 0, xn_per = 0, prp_x = 0, acct = 0, phi = 0;
+    double ptot = 1, pb = 0, pperp = 0, x = 0, prp_x = 0, acct = 0, phi = 0;
     double gam_pf = 1, gd = 0, grt = 0, gr = 0, gper = 0, t_step = 0, inv_ptot = 1, inv_gm = 1;
     double ux = 0, gsf = 1, gef = 1, bsin = 0, bcos = 1;
     int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1, xsel = 0;
-    bool down = false, inj = false;
-    long long retro_steps = 0;
-    unsigned long long tot_helix = 0, tot_retro = 0;
+    bool down = false, inj = false, x_old_le0 = true;
     int qn = 0;  // events queued by this warp (warp-uniform)
-    Rng rng;
+    Rng rng;  // only ever passed to force-inlined helpers from here: stays in registers
     rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
     int slot = -1;
 
@@ -734,13 +771,14 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 long long j = base + rank;
                 long long mine = dynamic ? j : ((j >> 5) * total_warps + gwarp) * 32 + (j & 31);
                 if (mine < P.n_use) {
-                    ip = mine;
+                    ip = (int)mine;
                     // particle_loop.jl:44-96, 131-153
-                    weight = P.cur.weight[ip]; ptot = P.cur.ptot[ip]; pb = P.cur.pb[ip]; x = P.cur.x[ip];
-                    xn_per = P.cur.xn_per[ip]; prp_x = P.cur.prp_x[ip]; acct = P.cur.acctime[ip]; phi = P.cur.phi[ip];
+                    ptot = P.cur.ptot[ip]; pb = P.cur.pb[ip]; x = P.cur.x[ip];
+                    const double xn_per = P.cur.xn_per[ip];
+                    prp_x = P.cur.prp_x[ip]; acct = P.cur.acctime[ip]; phi = P.cur.phi[ip];
                     i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
                     down = P.cur.down[ip]; inj = P.cur.inj[ip];
-                    helix = 0; i_return = -1; t_step = 0.0; x_old = 0.0; retro_steps = 0;
+                    helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0;
                     xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
                     gam_pf = hypot(1.0, ptot / P.mc);
                     gd = 1 / (P.zz * P.bt[i_grid]);
@@ -772,6 +810,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         int fin = -1;          // -1 running; 0 saved; 1..4 i_reason; 5 error
         uint32_t ev = 0;       // crossing event to queue at point A
         bool moved = false;
+        double x_old = 0.0;    // position before this pass's move
         if (ip >= 0) {
             helix++;
             if (MCS_UNLIKELY(helix > P.helix_cap)) {
@@ -794,13 +833,19 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                     gd = 1 / (P.zz * bmag);
                 }
                 if (MCS_UNLIKELY(zc && ux != P.ux[iz_old])) {
-                    transform_p_PSP(P, iz_old, iz, ptot, pb, pperp, gam_pf, phi);
+                    Mom mi;
+                    mi.ptot = ptot; mi.pb = pb; mi.pperp = pperp; mi.gam_pf = gam_pf; mi.phi = phi;
+                    const Mom mo = transform_p_PSP(P, iz_old, iz, mi);
+                    ptot = mo.ptot; pb = mo.pb; pperp = mo.pperp; gam_pf = mo.gam_pf; phi = mo.phi;
                     gr = pperp * P.c * gd;
                     grt = ptot * P.c * gd;
                     inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
                 }
-                if (MCS_UNLIKELY(P.energy_transfer_frac > 0 && !inj && x_old <= 0 && i_grid_old != i_grid)) {
-                    do_energy_transfer(P, i_grid, i_grid_old, ptot, pb, pperp, gam_pf, weight);
+                if (MCS_UNLIKELY(P.energy_transfer_frac > 0 && !inj && x_old_le0 && i_grid_old != i_grid)) {
+                    Mom mi;
+                    mi.ptot = ptot; mi.pb = pb; mi.pperp = pperp; mi.gam_pf = gam_pf; mi.phi = phi;
+                    const Mom mo = do_energy_transfer(P, i_grid, i_grid_old, mi, P.cur.weight[ip]);
+                    ptot = mo.ptot; pb = mo.pb; pperp = mo.pperp; gam_pf = mo.gam_pf;
                     inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
                 }
                 if (dont_scatter && x > 10 * gr) {
@@ -832,7 +877,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         else gper = TWO_PI * gam_pf * P.mc * gd;
                         double omc;
                         if (xsel < 2) omc = P.omc[xsel];
-                        else omc = 1 - cos(sqrt(6 * TWO_PI / (xn_per * P.eta_mfp)));
+                        else omc = 1 - cos(sqrt(6 * TWO_PI / (P.cur.xn_per[ip] * P.eta_mfp)));
                         double u1, u2;
                         uniform2<DEBUG>(rng, P, u1, u2);
                         const double cos_old = pb * inv_ptot, sin_old = pperp * inv_ptot;
@@ -856,16 +901,12 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                     if (down) {
                         acct += t_step * gef;
                         if (MCS_UNLIKELY((flags & F_TCUTS) && tcut <= P.n_tcuts && acct >= P.tcuts[tcut - 1])) {
-                            tcut_track(P, tcut, weight, ptot);
+                            tcut_track(P, tcut, P.cur.weight[ip], ptot);
                             tcut++;
                         }
                         if (MCS_UNLIKELY(ptot > P.pcut)) fin = 0;  // saved below
                     }
-                    if (fin < 0) {
-                        const bool coarse = x > grt;
-                        xn_per = coarse ? P.xn_coarse : P.xn_fine;
-                        xsel = coarse ? 1 : 0;
-                    }
+                    if (fin < 0) xsel = x > grt ? 1 : 0;  // xn_per = coarse : fine (particle_loop.jl:385)
                 }
             }
             if (MCS_LIKELY(fin < 0)) {
@@ -874,15 +915,22 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 x_old = x;
                 const double phi_old = phi;
                 double dphi;
-                if (xsel < 2) { t_step = gper * P.inv_xn[xsel]; dphi = P.dphi[xsel]; }
-                else { t_step = gper / xn_per; dphi = TWO_PI / xn_per; }
+                if (MCS_LIKELY(xsel < 2)) { t_step = gper * P.inv_xn[xsel]; dphi = P.dphi[xsel]; }
+                else { const double xn_per = P.cur.xn_per[ip]; t_step = gper / xn_per; dphi = TWO_PI / xn_per; }
                 phi = mod2pi(phi + dphi);
                 const double x_move = pb * t_step * inv_gm;
                 const double gyr = MCS_UNLIKELY(bsin != 0.0) ? gr * bsin * (cos_bf(phi) - cos_bf(phi_old)) : 0.0;
                 x = x_old + gsf * (x_move * bcos - gyr + ux * t_step);
                 bool err = false;
-                if (MCS_UNLIKELY(x <= 0 && x_old > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)))
-                    err = reflect_loop<DEBUG>(P, rng, pb, phi, x, x_old, phi_old, dphi, t_step, inv_gm, gsf, bcos, bsin, gr, ux);
+                if (MCS_UNLIKELY(x <= 0 && x_old > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1))) {
+                    ColdIO io;
+                    io.x = x; io.pb = pb; io.phi = phi; io.rng_n = rng.n; io.rng_s2 = rng.s2; io.rng_s3 = rng.s3;
+                    io.exhausted = rng.exhausted;
+                    const ColdIO o = reflect_loop<DEBUG>(P, io, x_old, phi_old, dphi, t_step, inv_gm, gsf, bcos, bsin, gr, ux,
+                                                         rng.c1, rng.ru, rng.rn);
+                    x = o.x; pb = o.pb; phi = o.phi; err = o.err;
+                    rng.n = o.rng_n; rng.s2 = o.rng_s2; rng.s3 = o.rng_s3; rng.exhausted = o.exhausted;
+                }
                 if (MCS_UNLIKELY(x_old < 0 && x >= 0)) {
                     down = true;
                     double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
@@ -929,7 +977,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             if (m) {
                 if (ev) {
                     const int q = qn + __popc(m & ((1u << lane) - 1u));
-                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = weight;
+                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = P.cur.weight[ip];
                     wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
                 }
                 qn += __popc(m);
@@ -951,8 +999,16 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             if (MCS_LIKELY(!special)) {
                 i_return = 2;
             } else {
-                fin = downstream_block<DEBUG, ELECTRON>(P, rng, x, x_old, prp_x, ptot, pb, pperp, gam_pf, gd, grt, acct, phi,
-                                                        weight, tcut, helix, i_return, retro_steps, went_retro, lose_pt);
+                ColdIO io;
+                io.x = x; io.prp_x = prp_x; io.ptot = ptot; io.pb = pb; io.pperp = pperp; io.gam_pf = gam_pf; io.gd = gd;
+                io.acct = acct; io.phi = phi; io.retro_steps = 0; io.rng_n = rng.n; io.rng_s2 = rng.s2;
+                io.rng_s3 = rng.s3; io.tcut = tcut; io.i_return = i_return; io.exhausted = rng.exhausted;
+                const ColdIO o = downstream_block<DEBUG, ELECTRON>(P, io, x_old, grt, P.cur.weight[ip], helix, rng.c1, rng.ru,
+                                                                   rng.rn);
+                x = o.x; prp_x = o.prp_x; ptot = o.ptot; pb = o.pb; pperp = o.pperp; gam_pf = o.gam_pf; gd = o.gd;
+                acct = o.acct; phi = o.phi; if (o.retro_steps) P.retro[ip] += o.retro_steps; rng.n = o.rng_n; rng.s2 = o.rng_s2;
+                rng.s3 = o.rng_s3; tcut = o.tcut; i_return = o.i_return; fin = o.fin; went_retro = o.went_retro;
+                lose_pt = o.lose_pt; rng.exhausted = o.exhausted;
                 if (went_retro && ELECTRON) { inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m); }
             }
             if (DEBUG && slot >= 0 && fin < 0) {
@@ -969,25 +1025,27 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             if (fin < 0 && i_return == 0) { sum_p = true; fin = lose_pt ? 4 : 1; }
             if (DEBUG && fin < 0 && rng.exhausted) fin = MCS_FATE_ERROR;
         }
+        if (moved) x_old_le0 = x_old <= 0.0;
         // ---- point B (converged): particles that left the loop ------------------------------------------------
         ev = 0;
         if (MCS_UNLIKELY(ip >= 0 && fin >= 0)) {
             if (DEBUG && rng.exhausted) { fin = MCS_FATE_ERROR; sum_p = false; }
             if (fin == 0) {  // particle_loop.jl:361-380
                 P.l_save[ip] = 1;
-                P.saved.weight[ip] = weight; P.saved.ptot[ip] = ptot; P.saved.pb[ip] = pb; P.saved.x[ip] = x;
+                P.saved.weight[ip] = P.cur.weight[ip]; P.saved.ptot[ip] = ptot; P.saved.pb[ip] = pb; P.saved.x[ip] = x;
                 P.saved.grid[ip] = i_grid; P.saved.down[ip] = down; P.saved.inj[ip] = inj;
-                P.saved.xn_per[ip] = xn_per; P.saved.prp_x[ip] = x < prp_x ? prp_x : x * 1.1;
+                P.saved.xn_per[ip] = xsel == 0 ? P.xn_fine : (xsel == 1 ? P.xn_coarse : P.cur.xn_per[ip]);
+                P.saved.prp_x[ip] = x < prp_x ? prp_x : x * 1.1;
                 P.saved.acctime[ip] = acct; P.saved.phi[ip] = phi; P.saved.tcut[ip] = tcut;
             } else if (fin <= 4) {
                 ev = EV_VALID | EV_FINISH | ((uint32_t)fin << EV_REASON_SHIFT) | (sum_p ? EV_SUMP : 0u);
             } else {
                 count(P, CNT_ERR);
             }
-            P.fate[ip] = fin; P.helix[ip] = helix; P.retro[ip] = retro_steps; P.draws[ip] = rng.n;
+            P.fate[ip] = fin; P.helix[ip] = helix; P.draws[ip] = rng.n;
             count(P, CNT_FATE0 + fin);
-            tot_helix += (unsigned long long)helix;
-            tot_retro += (unsigned long long)retro_steps;
+            count(P, CNT_HELIX, (unsigned long long)helix);
+            { const long long rs = P.retro[ip]; if (rs) count(P, CNT_RETRO, (unsigned long long)rs); }
             ip = -1;
         }
         {
@@ -995,7 +1053,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             if (m) {
                 if (ev) {
                     const int q = qn + __popc(m & ((1u << lane) - 1u));
-                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = weight;
+                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = P.cur.weight[ip];
                     wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
                 }
                 qn += __popc(m);
@@ -1010,15 +1068,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     __syncwarp();
     if (qn > 0) process_events(P, wm, 0, qn);
 
-    // ---- warp totals, block partials ----------------------------------------------------------------
-    for (int o = 16; o > 0; o >>= 1) {
-        tot_helix += __shfl_xor_sync(FULL, tot_helix, o);
-        tot_retro += __shfl_xor_sync(FULL, tot_retro, o);
-    }
-    if (lane == 0) {
-        if (tot_helix) count(P, CNT_HELIX, tot_helix);
-        if (tot_retro) count(P, CNT_RETRO, tot_retro);
-    }
+    // ---- block partials -------------------------------------------------------------------------------
     __syncthreads();
     const int np = 4 * ng + SC_N;
     double* part = P.t.block_partials + (size_t)blockIdx.x * (size_t)np;

@@ -35,6 +35,14 @@ def test_cuda_library_exports_abi():
     assert lib.mcs_backend().decode() == "cuda-sm_100a"
 
 
+def test_cuda_library_is_not_stale():
+    """A failed nvcc build must not leave an older libmcs_b200.so in place unnoticed."""
+    src = os.path.join(ROOT, "montecarloscattering.jl_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src) if f.endswith((".cu", ".cuh")))
+    newest = max(newest, os.path.getmtime(os.path.join(ROOT, "include", "mcs.h")))
+    assert os.path.getmtime(mcs_b200.lib_path()) >= newest, "libmcs_b200.so is older than its sources: rebuild"
+
+
 def test_default_config_identical(olib):
     lib = abi.bind(C.CDLL(mcs_b200.lib_path()))
     a, b = abi.default_config(olib), abi.default_config(lib)
