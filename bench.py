@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FLOP_PER_STEP = 185.0  # SURVEY.md 8d, Appendix D; restated in DESIGN.md
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE transport-kernel launch at 1e6 particles per pcut, from the
+# `ncu --set full` capture summarised in profiles/r01_v5_transport_kernel_summary.md (154.4 MB + 92.6 MB, launch 7 of 11).
+# Algorithmic bytes of that launch: 1e6 particles x (82 B in + 83 B out) = 165 MB; the rest is PSD / log atomics.
+NCU_DRAM_BYTES_PER_LAUNCH_1E6 = 247.0e6
 METRIC = "scattering_steps_per_sec"
 
 
@@ -265,7 +269,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "transport_kernel<false>", "achieved": achieved, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E6 * a.n_per_pcut / 1e6 if a.workload == "planar" else None,
+                         "traffic_source": "ncu --set full capture at 1e6 particles per pcut (profiles/), scaled by particle count",
                          "flop_per_step": FLOP_PER_STEP, "kernel_ms_per_launch": kern_s * 1e3 / max(tm["transport_launches"], 1),
                          "kernel_share_of_step": kern_s / dev_s,
                          "peak_source": "measured live: DFMA microbenchmark in libmcs_b200.so (MEASURED_PEAKS.json has no FP64 entry)"},
