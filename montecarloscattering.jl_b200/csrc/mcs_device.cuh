@@ -1028,6 +1028,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         if (moved) x_old_le0 = x_old <= 0.0;
         // ---- point B (converged): particles that left the loop ------------------------------------------------
         ev = 0;
+        bool release = false;
         if (MCS_UNLIKELY(ip >= 0 && fin >= 0)) {
             if (DEBUG && rng.exhausted) { fin = MCS_FATE_ERROR; sum_p = false; }
             if (fin == 0) {  // particle_loop.jl:361-380
@@ -1046,7 +1047,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             count(P, CNT_FATE0 + fin);
             count(P, CNT_HELIX, (unsigned long long)helix);
             { const long long rs = P.retro[ip]; if (rs) count(P, CNT_RETRO, (unsigned long long)rs); }
-            ip = -1;
+            release = true;  // ip is still needed by the event push below (weight is read from the population array)
         }
         {
             const unsigned m = __ballot_sync(FULL, ev != 0u);
@@ -1059,6 +1060,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 qn += __popc(m);
             }
         }
+        if (release) ip = -1;
         if (qn >= 32) {  // drain a full batch (sums commute; the order is fixed by the lock-step schedule)
             __syncwarp();
             process_events(P, wm, qn - 32, 32);

@@ -46,7 +46,7 @@ def natural_scales(run, sp, pop):
     }
 
 
-def compare_saved(run, sp, a, b, tol):
+def compare_saved(run, sp, a, b, tol, tol_phi=None):
     """a, b: get_population(1, n) of oracle and device. Returns dict field -> max scaled difference."""
     assert np.array_equal(a["l_save"], b["l_save"]), "l_save differs"
     m = a["l_save"].astype(bool)
@@ -61,7 +61,8 @@ def compare_saved(run, sp, a, b, tol):
             s = np.maximum(np.abs(x), 1e-300)
         s = np.where(s > 0, s, 1.0)
         out[nm] = float(np.max(np.abs(x - y) / s)) if x.size else 0.0
-        assert out[nm] <= tol, f"{nm}: scaled difference {out[nm]:.3e} > {tol:g}"
+        lim = tol_phi if (nm == "phi_rad" and tol_phi is not None) else tol
+        assert out[nm] <= lim, f"{nm}: scaled difference {out[nm]:.3e} > {lim:g}"
     return out
 
 

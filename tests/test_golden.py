@@ -43,4 +43,4 @@ def test_oracle_reproduces_golden(olib, name):
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_cuda_reproduces_golden(clib, name):
     mk, ion = CASES[name]
-    check(run_case(clib, mk(), ion), name, ftol=1e-6)
+    check(run_case(clib, mk(), ion), name, ftol=1e-8)

@@ -2,8 +2,10 @@
 
 Bar (BASELINE.json north_star): integer decisions — zone, pcut/save, escape reason, pass counts, number of
 uniforms drawn, crossing counts — bit-exact; continuous state within 1e-12 relative in replay mode, measured on
-each quantity's natural scale (helpers.natural_scales).  After thousands of chaotic scattering steps the two
-libms (CUDA vs glibc: <= 2 ulp apart per call) have random-walked apart, so end-of-pcut state is held to 1e-9.
+each quantity's natural scale (helpers.natural_scales).  Measured on B200 (printed with -s): over whole pcuts (up to 1e4
+passes) x, ptot, pb, prp_x, acctime stay within 4e-12; the gyro-phase phi is the one ill-conditioned quantity — it
+accumulates asin(s) with |s| clamped at prevfloat(1.0) (scattering.jl:93-101), whose derivative 1/sqrt(1-s^2) reaches 1e8 —
+and is held to 1e-11 in replay and 1e-8 at the end of a pcut (measured 2e-12 and 7e-10).
 """
 import ctypes as C
 
@@ -16,8 +18,10 @@ from mcs_b200 import abi, driver, problem
 
 pytestmark = pytest.mark.gpu
 
-TOL_END_STATE = 1e-6
+TOL_END_STATE = 1e-10
+TOL_END_STATE_PHI = 1e-8
 TOL_REPLAY = 1e-12
+TOL_REPLAY_PHI = 1e-11
 TOL_TALLY = 1e-8
 REPLAY_WINDOW = 100
 
@@ -49,7 +53,7 @@ def test_per_particle_parity(olib, clib, name):
             for key in ("fate", "helix_count", "retro_steps", "n_draws"):
                 assert np.array_equal(fo[key], fc[key]), f"{name} ion {i_ion} pcut {k}: {key} differs"
             assert (ns_o, st_o) == (ns_c, st_c)
-            d = compare_saved(run, sp, eo.get_population(1, n), ec.get_population(1, n), TOL_END_STATE)
+            d = compare_saved(run, sp, eo.get_population(1, n), ec.get_population(1, n), TOL_END_STATE, TOL_END_STATE_PHI)
             for kk, v in d.items():
                 worst[kk] = max(worst.get(kk, 0.0), v)
             if ns_o == 0:
@@ -143,18 +147,18 @@ def test_replay_mode_trajectories(olib, clib, name):
                        ("phi_rad", 2 * np.pi), ("prp_x_cm", sc_["prp_x_cm"]),
                        ("acctime_sec", np.maximum(np.abs(a["acctime_sec"]), 1e-300))):
             e_all = np.abs(a[key] - b[key]) / s
-            for w, lim in ((25, None), (100, None), (400, None)):
+            for w, lim in ((25, None), (50, None), (100, None), (400, None)):
                 growth.setdefault((key, w), 0.0)
                 growth[(key, w)] = max(growth[(key, w)], float(e_all[:w].max()))
             err = float(e_all[:REPLAY_WINDOW].max())
             worst = max(worst, err)
             assert err <= TOL_REPLAY, f"{key}: {err:.3e} over the first {REPLAY_WINDOW} passes"
     print(f"\n[{name}] replay: worst scaled trajectory difference over the first {REPLAY_WINDOW} passes x {len(idx)} particles = {worst:.2e}")
-    print("   growth (max scaled difference within the first 25 / 100 / 400 passes):")
+    print("   growth (max scaled difference within the first 25 / 50 / 100 / 400 passes):")
     for key in ("x_cm", "ptot_pf", "pb_pf", "phi_rad", "prp_x_cm", "acctime_sec"):
-        print(f"   {key:12s} " + "  ".join(f"{growth[(key, w)]:.1e}" for w in (25, 100, 400)))
+        print(f"   {key:12s} " + "  ".join(f"{growth[(key, w)]:.1e}" for w in (25, 50, 100, 400)))
     assert n_traced >= 12
-    compare_saved(run, sp, so, sc, TOL_END_STATE)
+    compare_saved(run, sp, so, sc, TOL_END_STATE, TOL_END_STATE_PHI)
 
 
 def test_device_pcut_loop_matches_host_loop(clib):

@@ -52,11 +52,14 @@ def compare(inp, label, n_pcuts=None, seed=210):
         d = np.abs(a-b); s = np.maximum(np.abs(a), np.abs(b)); s[s == 0] = 1
         return float((d/s).max()) if a.size else 0.0
     for nm in ("pxx_flux","pxz_flux","energy_flux","psd","esc_psd_feb_upstream","esc_psd_feb_downstream","esc_energy_eff","esc_num_eff","weight_coupled","spectra_coupled","energy_transfer_pool"):
+        ok &= rel(getattr(t0,nm), getattr(t1,nm)) < 1e-8
         print(f"   {nm:26s} rel diff {rel(getattr(t0,nm), getattr(t1,nm)):.2e}  sum {getattr(t0,nm).sum():.6e} / {getattr(t1,nm).sum():.6e}")
     print("   num_crossings equal:", bool((t0.num_crossings == t1.num_crossings).all()), " log", len(t0.therm_grid), len(t1.therm_grid))
     k0 = np.lexsort((t0.therm_weight, t0.therm_ptot_sk, t0.therm_px_sk, t0.therm_grid)); k1 = np.lexsort((t1.therm_weight, t1.therm_ptot_sk, t1.therm_px_sk, t1.therm_grid))
     if len(k0) == len(k1) and len(k0):
         print("   log sorted: grid equal", bool((t0.therm_grid[k0] == t1.therm_grid[k1]).all()), "px rel", rel(t0.therm_px_sk[k0], t1.therm_px_sk[k1]), "w rel", rel(t0.therm_weight[k0], t1.therm_weight[k1]))
+    for k in t0.scalars: ok &= abs(t0.scalars[k]-t1.scalars[k]) <= 1e-9*abs(t0.scalars[k])
+    ok &= t0.stats == t1.stats and bool((t0.num_crossings == t1.num_crossings).all())
     print("   scalars", {k: (t0.scalars[k], t1.scalars[k]) for k in t0.scalars})
     print("   stats", t0.stats, "\n        ", t1.stats)
     print("   timing", engs[1].timing())
