@@ -60,7 +60,8 @@ def workload_config(workload, run, n_per_pcut, extra=None):
          "pcuts_mpc": [float(p) for p in run.inp.momentum_cutoffs], "n_grid": run.n_grid,
          "psd_bins": [run.num_psd_mom_bins + 2, run.num_psd_theta_bins + 2, run.n_grid],
          "xn_per": [run.inp.fine_scattering_Ng, run.inp.coarse_scattering_Ng], "rng": "philox4x32-10 seed 210",
-         "step": "one iteration of one ion species (all pcuts)"}
+         "step": "one iteration of one ion species (all pcuts)",
+         "population_order": "momentum-sorted injection list dealt into 64 strided sub-sequences (balances contiguous rank shards)"}
     if extra:
         c.update(extra)
     return c
@@ -114,7 +115,7 @@ def cpu_arm(workload, sample_per_pcut, steps, warmup, threads):
     tot_steps, tot_t = 0, 0.0
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        r = driver.main_loops(run, e, n_iters=1, want_psd=True, want_log=False)[0][0]
+        r = driver.main_loops(run, e, n_iters=1, want_psd=True, want_log=False, shuffle_population=True)[0][0]
         dt = time.perf_counter() - t0
         st = r["tallies"].stats["n_helix_steps"] + r["tallies"].stats["n_retro_steps"]
         if it >= warmup:
@@ -202,7 +203,7 @@ def main():
         eng.comm_init(rank, world, bytes(uid.cpu().tolist()))
 
     # host inputs of one step, in pinned memory (the population main_loops.jl hands to the particle loop)
-    ip = problem.init_pop(run, prof, 1, np.random.default_rng(0))
+    ip = problem.init_pop(run, prof, 1, np.random.default_rng(0), shuffle=True)
     lo, hi = driver.shard_bounds(len(ip.pop["weight"]), rank, world)
     pinned, pop = [], {}
     for k, v in ip.pop.items():

@@ -144,7 +144,7 @@ def reduce_tallies_host(t: abi.Tallies, comm) -> abi.Tallies:
 
 def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = None, comm=None,
                device_comm: bool = False, want_psd: bool = True, want_log: bool = True, profile_update=None,
-               host_pcut_loop: bool = False):
+               host_pcut_loop: bool = False, shuffle_population: bool = False):
     """loop_itr / loop_ion / loop_pcut of main_loops.jl:52-341.
 
     Returns a list (per iteration) of lists (per ion) of dicts with the per-ion tallies (pure sums),
@@ -167,7 +167,7 @@ def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = No
                 per_ion.append(None)
                 continue
             rng = np.random.default_rng((i_iter - 1) * run.n_ions + (i_ion - 1))  # stands in for :120-121
-            ip = problem.init_pop(run, prof, i_ion, rng)
+            ip = problem.init_pop(run, prof, i_ion, rng, shuffle=shuffle_population)
             n = len(ip.pop["weight"])
             lo, hi = shard_bounds(n, rank, world)
             pop = {k: v[lo:hi] for k, v in ip.pop.items()}

@@ -607,7 +607,7 @@ class InitPop:
     weight_running: float
 
 
-def init_pop(run: Run, prof: Profile, i_ion: int, rng: np.random.Generator) -> InitPop:
+def init_pop(run: Run, prof: Profile, i_ion: int, rng: np.random.Generator, shuffle: bool = False) -> InitPop:
     """init_pop (initializers.jl:977-1134), F_update! (:1157-1223) and the phase draw of
     assign_particle_properties_to_population! (ion_init.jl:51). `rng` replaces Random.Xoshiro of
     main_loops.jl:120-121 (host side, outside the replaced region): one uniform block for pb (or one
@@ -678,6 +678,16 @@ def init_pop(run: Run, prof: Profile, i_ion: int, rng: np.random.Generator) -> I
             vx_sf = vmin + (vmax - vmin) * np.sqrt(r)
             pb = 1.0 * m * (vx_sf - u)
     phi = 2 * math.pi * rng.random(n)
+    if shuffle:
+        # The reference orders the injected particles by momentum bin.  Sharding contiguous index blocks over GPUs
+        #  then gives rank 0 the slow half and the last rank the fast half of the Maxwellian, i.e. unequal
+        # numbers of survivors per rank.  A fixed permutation (independent of the rank count) removes that; the order
+        # only decides which RNG counter a particle gets.  The permutation is 64 strided sub-sequences laid end to end
+        # (indices 0,64,128,... then 1,65,...): any block of n/W particles (W = 1,2,4,8,...,64 ranks) is a fair sample
+        # of the Maxwellian AND stays momentum-sorted inside, which keeps the lanes of a warp on similar trajectories
+        # (a random shuffle costs 3 % on one GPU).
+        perm = np.concatenate([np.arange(k, n, 64) for k in range(64)])
+        w, ptot, pb, x, grid, phi = w[perm], ptot[perm], pb[perm], x[perm], grid[perm], phi[perm]
     pop = dict(weight=w, ptot_pf=ptot, pb_pf=pb, x_cm=x, grid=grid, phi_rad=phi)
     return InitPop(pop=pop, pxx_flux=pxx, pxz_flux=pxz, energy_flux=efl, weight_running=float(w[0]) if n else 0.0)
 
