@@ -267,6 +267,9 @@ MCS_API int mcs_get_timing(McsHandle* h, McsTiming* out, int32_t reset);
  * (MEASURED_PEAKS.json has no FP64 entry): DFMA TFLOP/s and scattered FP64 atomicAdd G-ops/s. */
 MCS_API int mcs_measure_fp64_peak(McsHandle* h, double* tflops);
 MCS_API int mcs_measure_atomic_peak(McsHandle* h, int64_t n_cells, double* gops);
+/* Rate [steps/s] of the bare arithmetic of one bulk scattering step (Philox + kick + phase + move)
+ * with no control flow around it: the practical ceiling of the transport kernel's hot path on this device. */
+MCS_API int mcs_measure_scatter_peak(McsHandle* h, double* steps_per_s);
 
 #ifdef __cplusplus
 }

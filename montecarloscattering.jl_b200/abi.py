@@ -111,7 +111,7 @@ ABI_SYMBOLS = (
     "mcs_comm_unique_id", "mcs_comm_init", "mcs_set_profile", "mcs_begin_ion", "mcs_run_pcut", "mcs_split", "mcs_split_explicit",
     "mcs_run_ion", "mcs_end_ion", "mcs_get_population", "mcs_population_size", "mcs_get_fates",
     "mcs_replay_set_stream", "mcs_trace_enable", "mcs_trace_get", "mcs_get_timing", "mcs_measure_fp64_peak",
-    "mcs_measure_atomic_peak",
+    "mcs_measure_atomic_peak", "mcs_measure_scatter_peak",
 )
 
 
@@ -154,6 +154,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mcs_get_timing.argtypes = [H, C.POINTER(McsTiming), _i32]
     lib.mcs_measure_fp64_peak.argtypes = [H, _pd]
     lib.mcs_measure_atomic_peak.argtypes = [H, _i64, _pd]
+    lib.mcs_measure_scatter_peak.argtypes = [H, _pd]
     sizes = (_i32 * 6)()
     lib.mcs_abi_sizes(C.byref(sizes))
     want = [C.sizeof(t) for t in (McsConfig, McsSpecies, McsTallies, McsPopulation, McsTraceRec, McsTiming)]
@@ -376,6 +377,11 @@ class Engine:
     def measure_fp64_peak(self) -> float:
         v = _d()
         self._check(self.lib.mcs_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_scatter_peak(self) -> float:
+        v = _d()
+        self._check(self.lib.mcs_measure_scatter_peak(self._h, C.byref(v)))
         return v.value
 
     def measure_atomic_peak(self, n_cells: int) -> float:

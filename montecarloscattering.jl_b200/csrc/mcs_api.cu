@@ -272,7 +272,8 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     P.flags = (cfg->do_rad_losses ? F_RAD_LOSSES : 0) | (cfg->do_retro ? F_RETRO : 0) | (cfg->do_tcuts ? F_TCUTS : 0) |
               (cfg->dont_DSA ? F_DONT_DSA : 0) | (cfg->dont_scatter ? F_DONT_SCATTER : 0) |
               (cfg->use_custom_epsB ? F_CUSTOM_EPSB : 0) | ((cfg->compat & MCS_COMPAT_RETRO_KEEP_NEW_PITCH) ? F_KEEP_NEW_PITCH : 0) |
-              ((cfg->dynamic_queue || env_int("MCS_DYNAMIC_QUEUE", 0)) ? F_DYNAMIC_QUEUE : 0);
+              ((cfg->dynamic_queue || env_int("MCS_DYNAMIC_QUEUE", 0)) ? F_DYNAMIC_QUEUE : 0) |
+              (env_int("MCS_NO_FAST_LOOP", 0) ? F_NO_FAST_LOOP : 0);
     {   // per-xn_per scattering constants, host libm (scattering.jl:46-60: the gyroradius cancels in vp_tg / lambda_mfp)
         const double xn[2] = {cfg->xn_per_fine, cfg->xn_per_coarse};
         for (int k = 0; k < 2; k++) {
@@ -753,5 +754,27 @@ extern "C" int mcs_measure_atomic_peak(McsHandle* h, int64_t n_cells, double* go
     }
     cudaFree(d);
     *gops = best;
+    return MCS_OK;
+}
+
+extern "C" int mcs_measure_scatter_peak(McsHandle* h, double* steps_per_s) {
+    if (!h || !steps_per_s) return fail(MCS_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int blocks = h->n_sm * 2, threads = 256, iters = 20000;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)blocks * threads * 8));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(h->ev2, h->stream));
+        scatter_only_kernel<<<blocks, threads, 0, h->stream>>>(d, iters, h->P.omc[0], h->P.inv_xn[0], h->P.dphi[0], h->P.key0, h->P.key1);
+        CU(cudaEventRecord(h->ev3, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        double r = (double)iters * blocks * threads / (ms * 1e-3);
+        if (rep > 0 && r > best) best = r;
+    }
+    cudaFree(d);
+    *steps_per_s = best;
     return MCS_OK;
 }

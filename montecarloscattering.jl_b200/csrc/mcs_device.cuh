@@ -32,6 +32,12 @@
 #ifndef MCS_MIN_BLOCKS
 #define MCS_MIN_BLOCKS 2
 #endif
+#ifndef MCS_PARK_T
+#define MCS_PARK_T 8      // lanes that must be waiting (parked or refillable) before the warp leaves the fast loop
+#endif
+#ifndef MCS_FAST_MAX
+#define MCS_FAST_MAX 256  // safety bound on consecutive fast passes
+#endif
 
 namespace mcs {
 
@@ -47,7 +53,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 enum : uint32_t {
     F_RAD_LOSSES = 1u, F_RETRO = 2u, F_TCUTS = 4u, F_DONT_DSA = 8u, F_DONT_SCATTER = 16u, F_CUSTOM_EPSB = 32u,
-    F_KEEP_NEW_PITCH = 64u, F_DYNAMIC_QUEUE = 128u,
+    F_KEEP_NEW_PITCH = 64u, F_DYNAMIC_QUEUE = 128u, F_NO_FAST_LOOP = 256u,
 };
 
 // event flags
@@ -734,6 +740,8 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     const uint32_t flags = P.flags;
     const bool custom = flags & F_CUSTOM_EPSB, dont_scatter = flags & F_DONT_SCATTER, dynamic = flags & F_DYNAMIC_QUEUE;
     const bool rad = ELECTRON && (flags & F_RAD_LOSSES);
+    // the fast loop covers scattering configurations without per-pass field updates, detectors or debug streams
+    const bool fast_ok = !DEBUG && !custom && !rad && !dont_scatter && P.n_xspec == 0 && !(flags & F_NO_FAST_LOOP);
     const long long total_warps = (long long)gridDim.x * n_warps, gwarp = (long long)blockIdx.x * n_warps + warp;
 
     // lane state -------------------------------------------------------------------------------
@@ -747,6 +755,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     double ux = 0, gsf = 1, gef = 1, bsin = 0, bcos = 1;
     int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1, xsel = 0;
     bool down = false, inj = false, x_old_le0 = true;
+    bool parked = true;  // the lane's next pass must take the general path (see the fast loop below)
     int qn = 0;  // events queued by this warp (warp-uniform)
     Rng rng;  // only ever passed to force-inlined helpers from here: stays in registers
     rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
@@ -778,7 +787,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                     prp_x = P.cur.prp_x[ip]; acct = P.cur.acctime[ip]; phi = P.cur.phi[ip];
                     i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
                     down = P.cur.down[ip]; inj = P.cur.inj[ip];
-                    helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0;
+                    helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0; parked = true;
                     xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
                     gam_pf = hypot(1.0, ptot / P.mc);
                     gd = 1 / (P.zz * P.bt[i_grid]);
@@ -811,7 +820,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         uint32_t ev = 0;       // crossing event to queue at point A
         bool moved = false;
         double x_old = 0.0;    // position before this pass's move
-        if (ip >= 0) {
+        if (ip >= 0 && parked) {
             helix++;
             if (MCS_UNLIKELY(helix > P.helix_cap)) {
                 fin = 1;  // K-1
@@ -964,12 +973,14 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         }
         // crossing event? (all_flux.jl:80-82 early-out inverted), evaluated by every lane in converged code
         if (moved && fin < 0 && !(i_grid == i_grid_old && i_grid > P.i_grid_feb && P.n_xspec == 0)) {
-            ev = EV_VALID | (inj ? EV_INJ : 0u) | (x > x_old ? 0u : EV_UP) |
-                 ((inj && x < P.feb_up && x_old >= P.feb_up) ? EV_FEB_UP : 0u);
+            ev = (inj ? EV_INJ : 0u) | (x > x_old ? 0u : EV_UP) | ((inj && x < P.feb_up && x_old >= P.feb_up) ? EV_FEB_UP : 0u);
             for (int i = 0; i < P.n_xspec; i++) {
                 const double xs = P.x_spec[i];
                 if ((x_old < xs && x >= xs) || (x <= xs && x_old > xs)) ev |= 1u << (EV_XSPEC_SHIFT + i);
             }
+            // with the zone unchanged F_stream's range is empty: only the FEB scalars / x_spec spectra can be touched
+            if (i_grid != i_grid_old || (ev & (EV_FEB_UP | (0xffffu << EV_XSPEC_SHIFT)))) ev |= EV_VALID;
+            else ev = 0;
         }
         // ---- point A (converged): queue the crossing events with the state as it is right after the move ----
         {
@@ -1065,6 +1076,126 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             __syncwarp();
             process_events(P, wm, qn - 32, 32);
             qn -= 32;
+        }
+        parked = false;
+
+        // ---- FAST LOOP ------------------------------------------------------------------------------------------
+        // The bare arithmetic of a pass runs at 8e10 steps/s on B200 when it is a tight loop (scatter_only_kernel);
+        // the general pass above is ~2x the instructions spread over 32 KB of code and reaches IPC 0.3.  So passes in
+        // which NOTHING rare happens (no zone change, escape, save, tcut, reflection, shock crossing, PRP logic) are
+        // done here, in a loop small enough for the instruction cache.  A lane that meets anything rare commits
+        // nothing and PARKS; when MCS_PARK_T lanes are waiting the warp goes round the outer loop once and the
+        // general pass serves all of them together.  Per particle the sequence of operations is unchanged.
+        if (fast_ok) {
+            for (int it = 0; it < MCS_FAST_MAX; it++) {
+                uint32_t fev = 0;  // crossing event produced by this fast pass
+                if (ip >= 0 && !parked) {
+                    bool park = (helix >= P.helix_cap) | (i_return == 1) | (xsel > 1) |
+                                (P.energy_transfer_frac > 0 && !inj && x_old_le0 && i_grid_old != i_grid) |
+                                (ptot > P.pmax_cutoff) | (inj && x < P.feb_up) | (P.age_max > 0 && acct > P.age_max);
+                    if (i_grid != iz) {
+                        // Code Block 3 zone change: stays here unless the flow speed differs (then transform_p_PSP: general pass)
+                        if (P.ux[i_grid] != ux) park = true;
+                        else if (!park) {
+                            iz = i_grid;
+                            gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                            gd = 1 / (P.zz * P.bt[iz]);
+                        }
+                    }
+                    double acct_n = acct;
+                    if (down) {
+                        acct_n = acct + t_step * gef;
+                        park |= ((flags & F_TCUTS) && tcut <= P.n_tcuts && acct_n >= P.tcuts[tcut - 1]) | (ptot > P.pcut);
+                    }
+                    if (!park) {
+                        // scattering.jl:29-101 (same expressions as the general pass)
+                        double gper_n;
+                        if (ELECTRON && ptot < P.pe_crit) gper_n = TWO_PI * P.gam_e_crit * P.mc * gd;
+                        else gper_n = TWO_PI * gam_pf * P.mc * gd;
+                        const double omc = P.omc[xsel];
+                        // one Philox block per pass whether or not the stream is block-aligned
+                        const uint32_t odd = rng.n & 1u;
+                        uint32_t o0, o1, o2, o3;
+                        philox4x32_10((rng.n + odd) >> 1, rng.c1, P.ctr2, P.ctr3, P.key0, P.key1, o0, o1, o2, o3);
+                        const double u1 = odd ? u53(rng.s3, rng.s2) : u53(o1, o0);
+                        const double u2 = odd ? u53(o1, o0) : u53(o3, o2);
+                        const double cos_old = pb * inv_ptot, sin_old = pperp * inv_ptot;
+                        const double cos_d = 1 - u1 * omc;
+                        const double sd2 = 1 - cos_d * cos_d;
+                        const double phi_s = u2 * TWO_PI - PI;
+                        double sps, cps;
+                        sincos_bf(phi_s, &sps, &cps);
+                        const double sin_d = sqrt(sd2);
+                        const double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
+                        const double sn2 = 1 - cos_new * cos_new;
+                        const double sin_new = sqrt(sn2);
+                        double phi_p = phi + HALF_PI;
+                        {
+                            double sv = sps * sin_d / sin_new;
+                            if (fabs(sv) > SIN_UPPER_LIMIT) sv = copysign(SIN_UPPER_LIMIT, sv);
+                            phi_p += asin_bf(sv);
+                        }
+                        const double phi_sc = phi_p - HALF_PI;
+                        const double pb_n = ptot * cos_new, pperp_n = ptot * sin_new;
+                        // Code Block 2 move
+                        const int xsel_n = x > grt ? 1 : 0;
+                        const double t_n = gper_n * P.inv_xn[xsel_n];
+                        const double phi_n = mod2pi(phi_sc + P.dphi[xsel_n]);
+                        const double x_move = pb_n * t_n * inv_gm;
+                        const double gyr = MCS_UNLIKELY(bsin != 0.0) ? gr * bsin * (cos_bf(phi_n) - cos_bf(phi_sc)) : 0.0;
+                        const double x_n = x + gsf * (x_move * bcos - gyr + ux * t_n);
+                        // anything the general pass would have to act on after the move -> nothing is committed
+                        park = !(sd2 >= 0.0) | !(sn2 > 0.0) | !(x_n == x_n) |
+                               (x_n <= 0 && x > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)) |
+                               (x < 0 && x_n >= 0) | (down && x_n < 0 && !inj) |
+                               (P.feb_dn > 0 && x_n > P.feb_dn) | (x_n > 1.1 * prp_x) |
+                               (x_n >= P.x_grid_stop && (x < P.x_grid_stop || (x < prp_x && x_n >= prp_x) || ELECTRON));
+                        if (!park) {
+                            // zone search (all_flux.jl:65-82) and the crossing event
+                            const bool dn = x_n > x;
+                            int ig = i_grid;
+                            const double edge = P.xg[i_grid + (dn ? 1 : 0)];
+                            if (!(dn ? (edge > x_n) : (edge <= x_n))) {
+                                if (dn) { int k = i_grid + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig = k - 1; }
+                                else { int k = i_grid; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig = k; }
+                            }
+                            const bool feb_x = inj && x_n < P.feb_up && x >= P.feb_up;
+                            if (ig != i_grid || (feb_x && ig <= P.i_grid_feb))
+                                fev = EV_VALID | (inj ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
+                            helix++;
+                            acct = acct_n; gper = gper_n; t_step = t_n; xsel = xsel_n;
+                            pb = pb_n; pperp = pperp_n; phi = phi_n;
+                            x_old_le0 = x <= 0.0; x = x_n; i_grid_old = i_grid; i_grid = ig; i_return = 2;
+                            rng.n += 2; rng.s2 = o2; rng.s3 = o3;
+                        }
+                    }
+                    parked = park;
+                }
+                {   // converged: queue the crossing events of this fast pass (state right after the move, as at point A)
+                    const unsigned m = __ballot_sync(FULL, fev != 0u);
+                    if (m) {
+                        if (fev) {
+                            const int q = qn + __popc(m & ((1u << lane) - 1u));
+                            wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi;
+                            wm.q_w[q] = P.cur.weight[ip]; wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old;
+                            wm.q_iz[q] = iz; wm.q_flags[q] = fev;
+                        }
+                        qn += __popc(m);
+                        if (qn >= 32) {
+                            __syncwarp();
+                            process_events(P, wm, qn - 32, 32);
+                            qn -= 32;
+                        }
+                    }
+                }
+                const unsigned active = __ballot_sync(FULL, ip >= 0);
+                const unsigned waiting = __ballot_sync(FULL, (ip >= 0 && parked) || (ip < 0 && !queue_empty));
+                const int n_act = __popc(active), n_wait = __popc(waiting);
+                if (n_wait > 0 && n_wait >= min(MCS_PARK_T, (n_act + 1) >> 1)) break;
+                if (n_act == 0) break;
+            }
+        } else {
+            parked = true;
         }
     }
     __syncwarp();
@@ -1194,6 +1325,40 @@ __global__ void dfma_peak_kernel(double* out, int iters) {
         a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// The NECESSARY arithmetic of one bulk scattering step and nothing else: Philox block, pitch-angle kick,
+// phase advance, move.  No zone test, no escape tests, no tallies, no refill.  Its rate on this GPU is the practical
+// ceiling for the transport kernel's hot path and is reported next to the DFMA peak.
+__global__ void __launch_bounds__(256, 2) scatter_only_kernel(double* out, int iters, double omc, double inv_xn, double dphi,
+                                                             uint32_t key0, uint32_t key1) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double ptot = 1.0e-17, pb = 0.3e-17, pperp = sqrt(ptot * ptot - pb * pb), phi = 0.1, x = -1.0e12;
+    const double inv_ptot = 1 / ptot, gper = 6.5e3, inv_gm = 1 / 1.67e-24, ux = 1.0e9, gsf = 1.0;
+    double acc = 0.0;
+    for (int i = 0; i < iters; i++) {
+        uint32_t o0, o1, o2, o3;
+        philox4x32_10((uint32_t)i, tid, 2u, 1u, key0, key1, o0, o1, o2, o3);
+        const double u1 = u53(o1, o0), u2 = u53(o3, o2);
+        const double cos_old = pb * inv_ptot, sin_old = pperp * inv_ptot;
+        const double cos_d = 1 - u1 * omc;
+        const double sin_d = sqrt(fmax(1 - cos_d * cos_d, 0.0));
+        const double phi_s = u2 * TWO_PI - PI;
+        double sps, cps;
+        sincos_bf(phi_s, &sps, &cps);
+        const double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
+        const double sin_new = sqrt(fmax(1 - cos_new * cos_new, 0.0));
+        pb = ptot * cos_new;
+        pperp = ptot * sin_new;
+        double s = sps * sin_d / sin_new;
+        if (fabs(s) > SIN_UPPER_LIMIT) s = copysign(SIN_UPPER_LIMIT, s);
+        phi = (phi + HALF_PI + asin_bf(s)) - HALF_PI;
+        const double t_step = gper * inv_xn;
+        phi = mod2pi(phi + dphi);
+        x = x + gsf * (pb * t_step * inv_gm + ux * t_step);
+        acc += t_step;
+    }
+    out[tid] = x + phi + acc;
 }
 
 __global__ void atomic_peak_kernel(double* cells, long long n_cells, int iters) {
