@@ -623,6 +623,9 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     t->sum_P_downstream = sc[SC_SUMP]; t->sum_KE_downstream = sc[SC_SUMKE];
     t->px_esc_upstream = sc[SC_PX_ESC_UP]; t->energy_esc_upstream = sc[SC_EN_ESC_UP];
     const unsigned long long* c = h->h_counters;
+    if (env_int("MCS_SCHED_STATS", 0))
+        fprintf(stderr, "[mcs] lane-passes: fast %llu general %llu | warp iterations: fast %llu general %llu\n", c[CNT_FAST_LANE],
+                c[CNT_SLOW_LANE], c[CNT_FAST_ITER], c[CNT_SLOW_SEC]);
     t->n_helix_steps = (int64_t)c[CNT_HELIX]; t->n_retro_steps = (int64_t)c[CNT_RETRO];
     t->n_warn_pperp = (int64_t)c[CNT_W_PPERP]; t->n_warn_psd_mom = (int64_t)c[CNT_W_PSDMOM]; t->n_neg_sqrt = (int64_t)c[CNT_NEGSQRT];
     t->n_retro_capped = (int64_t)c[CNT_RETRO_CAP]; t->n_errors = (int64_t)c[CNT_ERR];

@@ -33,7 +33,7 @@
 #define MCS_MIN_BLOCKS 2
 #endif
 #ifndef MCS_PARK_T
-#define MCS_PARK_T 8      // lanes that must be waiting (parked or refillable) before the warp leaves the fast loop
+#define MCS_PARK_T 16     // lanes that must be waiting (parked or refillable) before the warp leaves the fast loop
 #endif
 #ifndef MCS_FAST_MAX
 #define MCS_FAST_MAX 256  // safety bound on consecutive fast passes
@@ -71,7 +71,8 @@ struct PopPtrs {  // SoA particle record (main_loops.jl:212-226)
 enum { SC_ESC_FLUX = 0, SC_PX_ESC_FEB, SC_EN_ESC_FEB, SC_SUMP, SC_SUMKE, SC_PX_ESC_UP, SC_EN_ESC_UP, SC_N = 8 };
 enum {
     CNT_HELIX = 0, CNT_RETRO, CNT_W_PPERP, CNT_W_PSDMOM, CNT_NEGSQRT, CNT_RETRO_CAP, CNT_ERR, CNT_FATE0,  // ..FATE5 = 12
-    CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_N = 24
+    CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_FAST_LANE = 17, CNT_FAST_ITER = 18, CNT_SLOW_SEC = 19,
+    CNT_SLOW_LANE = 20, CNT_N = 24
 };
 
 struct TallyPtrs {
@@ -756,6 +757,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1, xsel = 0;
     bool down = false, inj = false, x_old_le0 = true;
     bool parked = true;  // the lane's next pass must take the general path (see the fast loop below)
+    unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_slow_sec = 0, c_slow_lane = 0;  // scheduling statistics
     int qn = 0;  // events queued by this warp (warp-uniform)
     Rng rng;  // only ever passed to force-inlined helpers from here: stays in registers
     rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
@@ -820,7 +822,9 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         uint32_t ev = 0;       // crossing event to queue at point A
         bool moved = false;
         double x_old = 0.0;    // position before this pass's move
+        c_slow_sec++;
         if (ip >= 0 && parked) {
+            c_slow_lane++;
             helix++;
             if (MCS_UNLIKELY(helix > P.helix_cap)) {
                 fin = 1;  // K-1
@@ -1162,7 +1166,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                             const bool feb_x = inj && x_n < P.feb_up && x >= P.feb_up;
                             if (ig != i_grid || (feb_x && ig <= P.i_grid_feb))
                                 fev = EV_VALID | (inj ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
-                            helix++;
+                            helix++; c_fast_lane++;
                             acct = acct_n; gper = gper_n; t_step = t_n; xsel = xsel_n;
                             pb = pb_n; pperp = pperp_n; phi = phi_n;
                             x_old_le0 = x <= 0.0; x = x_n; i_grid_old = i_grid; i_grid = ig; i_return = 2;
@@ -1188,10 +1192,11 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         }
                     }
                 }
+                c_fast_iter++;
                 const unsigned active = __ballot_sync(FULL, ip >= 0);
                 const unsigned waiting = __ballot_sync(FULL, (ip >= 0 && parked) || (ip < 0 && !queue_empty));
                 const int n_act = __popc(active), n_wait = __popc(waiting);
-                if (n_wait > 0 && n_wait >= min(MCS_PARK_T, (n_act + 1) >> 1)) break;
+                if (n_wait > 0 && n_wait >= min(MCS_PARK_T, (3 * n_act + 3) >> 2)) break;
                 if (n_act == 0) break;
             }
         } else {
@@ -1201,6 +1206,8 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     __syncwarp();
     if (qn > 0) process_events(P, wm, 0, qn);
 
+    count(P, CNT_FAST_LANE, c_fast_lane); count(P, CNT_SLOW_LANE, c_slow_lane);
+    if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_slow_sec); }
     // ---- block partials -------------------------------------------------------------------------------
     __syncthreads();
     const int np = 4 * ng + SC_N;
