@@ -227,6 +227,8 @@ def main():
     for _ in range(a.warmup):
         one_step()
     fp64_peak = eng.measure_fp64_peak()
+    scatter_peak = eng.measure_scatter_peak()
+    atomic_peak = eng.measure_atomic_peak(run.n_grid * (run.num_psd_mom_bins + 2) * (run.num_psd_theta_bins + 2))
     eng.timing(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     wall, steps_local, d2h, n_run = 0.0, 0, 0, 0
@@ -275,7 +277,11 @@ def main():
                          "traffic_source": "ncu --set full capture at 1e6 particles per pcut (profiles/), scaled by particle count",
                          "flop_per_step": FLOP_PER_STEP, "kernel_ms_per_launch": kern_s * 1e3 / max(tm["transport_launches"], 1),
                          "kernel_share_of_step": kern_s / dev_s,
-                         "peak_source": "measured live: DFMA microbenchmark in libmcs_b200.so (MEASURED_PEAKS.json has no FP64 entry)"},
+                         "peak_source": "measured live: DFMA microbenchmark in libmcs_b200.so (MEASURED_PEAKS.json has no FP64 entry)",
+                         "hot_path_ceiling_steps_per_s": scatter_peak,
+                         "frac_of_hot_path_ceiling": kern_steps_per_s / scatter_peak if scatter_peak else None,
+                         "hot_path_ceiling_source": "measured live: scatter_only_kernel = Philox + kick + phase + move, no control flow",
+                         "fp64_red_scattered_gops": atomic_peak},
         }
         if world == 1 and not a.no_cpu_baseline:
             v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads)
