@@ -132,7 +132,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="planar", choices=["planar", "relativistic", "nonlinear", "multi"])
     ap.add_argument("--n-per-pcut", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=2500, help="particles per pcut of the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=10000, help="particles per pcut of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
 

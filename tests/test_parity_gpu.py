@@ -152,7 +152,7 @@ def test_replay_mode_trajectories(olib, clib, name):
                 growth[(key, w)] = max(growth[(key, w)], float(e_all[:w].max()))
             err = float(e_all[:REPLAY_WINDOW].max())
             worst = max(worst, err)
-            assert err <= TOL_REPLAY, f"{key}: {err:.3e} over the first {REPLAY_WINDOW} passes"
+            assert err <= (TOL_REPLAY_PHI if key == "phi_rad" else TOL_REPLAY), f"{key}: {err:.3e} over the first {REPLAY_WINDOW} passes"
     print(f"\n[{name}] replay: worst scaled trajectory difference over the first {REPLAY_WINDOW} passes x {len(idx)} particles = {worst:.2e}")
     print("   growth (max scaled difference within the first 25 / 50 / 100 / 400 passes):")
     for key in ("x_cm", "ptot_pf", "pb_pf", "phi_rad", "prp_x_cm", "acctime_sec"):
@@ -275,3 +275,47 @@ def test_two_gpu_nccl_matches_one_gpu(clib):
         assert np.array_equal(out[r]["n_saved"], one["n_saved"]) and out[r]["tallies"].stats["n_fate"] == one["tallies"].stats["n_fate"]
         assert rel_close(out[r]["pxx_flux"], one["pxx_flux"], 0) < 1e-11
         assert rel_close(out[r]["tallies"].psd, one["tallies"].psd, 0) < 1e-10
+
+
+def test_fast_loop_matches_general_path(clib, monkeypatch):
+    """The two-speed kernel (fast loop + lane parking) against the same kernel with every pass on the general path
+    (MCS_NO_FAST_LOOP=1): per particle the sequence of operations is the same, so integers are identical and the
+    continuous state agrees to rounding (the two code paths may contract FMAs differently)."""
+    inp = problem.planar_test_particle_input(20_000, momentum_cutoffs=LADDER[:5])
+    run = problem.setup_run(inp)
+    sp = run.species[0]
+    res = []
+    for no_fast in ("0", "1"):
+        monkeypatch.setenv("MCS_NO_FAST_LOOP", no_fast)
+        e = make_engine(clib, run)
+        start_ion(e, run)
+        out = []
+        for k, pcut in enumerate(run.pcuts, start=1):
+            n = e.population_size()
+            ns, steps = e.run_pcut(k, pcut, run.pcuts[k - 2] if k > 1 else 0.0)
+            out.append((ns, steps, e.get_fates(n), e.get_population(1, n)))
+            if ns == 0:
+                break
+            e.split(inp.n_pts_pcut)
+        res.append((out, e.end_ion()))
+    (fa, ta), (ga, tb) = res
+    assert len(fa) == len(ga)
+    for (ns1, st1, f1, s1), (ns2, st2, f2, s2) in zip(fa, ga):
+        assert (ns1, st1) == (ns2, st2)
+        for key in ("fate", "helix_count", "retro_steps", "n_draws"):
+            assert np.array_equal(f1[key], f2[key]), key
+        compare_saved(run, sp, s1, s2, TOL_END_STATE, TOL_END_STATE_PHI)
+    assert ta.stats == tb.stats and np.array_equal(ta.num_crossings, tb.num_crossings)
+    assert rel_close(ta.pxx_flux, tb.pxx_flux, 0) < 1e-11 and rel_close(ta.psd, tb.psd, 0) < 1e-9
+
+
+def test_deterministic_tallies_run_to_run(clib):
+    """Default (static) schedule: the per-warp / per-block partials are reduced in a fixed order, so the flux tallies and
+    scalars are bitwise identical run to run (the PSD takes L2 atomics and is only required to agree to rounding)."""
+    run = problem.setup_run(problem.planar_test_particle_input(30_000, momentum_cutoffs=LADDER[:4]))
+    a = driver.main_loops(run, make_engine(clib, run), n_iters=1, want_log=False)[0][0]["tallies"]
+    b = driver.main_loops(run, make_engine(clib, run), n_iters=1, want_log=False)[0][0]["tallies"]
+    for nm in ("pxx_flux", "pxz_flux", "energy_flux", "num_crossings"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+    assert a.scalars == b.scalars and a.stats == b.stats
+    assert rel_close(a.psd, b.psd, 0) < 1e-12
