@@ -624,8 +624,13 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     t->px_esc_upstream = sc[SC_PX_ESC_UP]; t->energy_esc_upstream = sc[SC_EN_ESC_UP];
     const unsigned long long* c = h->h_counters;
     if (env_int("MCS_SCHED_STATS", 0))
+    {
         fprintf(stderr, "[mcs] lane-passes: fast %llu general %llu | warp iterations: fast %llu general %llu\n", c[CNT_FAST_LANE],
                 c[CNT_SLOW_LANE], c[CNT_FAST_ITER], c[CNT_SLOW_SEC]);
+        fprintf(stderr, "[mcs] park reasons: cap %llu ret1 %llu psp %llu pmax %llu feb %llu pcut %llu other-pre %llu | shock %llu inj %llu stop %llu prp %llu beyond %llu reflect %llu other-post %llu\n",
+                c[CNT_PARK0], c[CNT_PARK0 + 1], c[CNT_PARK0 + 2], c[CNT_PARK0 + 3], c[CNT_PARK0 + 4], c[CNT_PARK0 + 5], c[CNT_PARK0 + 6],
+                c[CNT_PARK0 + 8], c[CNT_PARK0 + 9], c[CNT_PARK0 + 10], c[CNT_PARK0 + 11], c[CNT_PARK0 + 12], c[CNT_PARK0 + 13], c[CNT_PARK0 + 14]);
+    }
     t->n_helix_steps = (int64_t)c[CNT_HELIX]; t->n_retro_steps = (int64_t)c[CNT_RETRO];
     t->n_warn_pperp = (int64_t)c[CNT_W_PPERP]; t->n_warn_psd_mom = (int64_t)c[CNT_W_PSDMOM]; t->n_neg_sqrt = (int64_t)c[CNT_NEGSQRT];
     t->n_retro_capped = (int64_t)c[CNT_RETRO_CAP]; t->n_errors = (int64_t)c[CNT_ERR];

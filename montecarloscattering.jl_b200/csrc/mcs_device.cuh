@@ -72,7 +72,7 @@ enum { SC_ESC_FLUX = 0, SC_PX_ESC_FEB, SC_EN_ESC_FEB, SC_SUMP, SC_SUMKE, SC_PX_E
 enum {
     CNT_HELIX = 0, CNT_RETRO, CNT_W_PPERP, CNT_W_PSDMOM, CNT_NEGSQRT, CNT_RETRO_CAP, CNT_ERR, CNT_FATE0,  // ..FATE5 = 12
     CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_FAST_LANE = 17, CNT_FAST_ITER = 18, CNT_SLOW_SEC = 19,
-    CNT_SLOW_LANE = 20, CNT_N = 24
+    CNT_SLOW_LANE = 20, CNT_PARK0 = 24, CNT_N = 40  // CNT_PARK0..+15: why lanes left the fast loop (MCS_SCHED_STATS)
 };
 
 struct TallyPtrs {
@@ -1111,6 +1111,13 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         acct_n = acct + t_step * gef;
                         park |= ((flags & F_TCUTS) && tcut <= P.n_tcuts && acct_n >= P.tcuts[tcut - 1]) | (ptot > P.pcut);
                     }
+#ifdef MCS_PARK_REASONS
+                    if (park) {
+                        int why = helix >= P.helix_cap ? 0 : i_return == 1 ? 1 : (i_grid != iz && P.ux[i_grid] != ux) ? 2 :
+                                  (ptot > P.pmax_cutoff) ? 3 : (inj && x < P.feb_up) ? 4 : (down && ptot > P.pcut) ? 5 : 6;
+                        count(P, CNT_PARK0 + why);
+                    }
+#endif
                     if (!park) {
                         // scattering.jl:29-101 (same expressions as the general pass)
                         double gper_n;
@@ -1151,9 +1158,32 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         // anything the general pass would have to act on after the move -> nothing is committed
                         park = !(sd2 >= 0.0) | !(sn2 > 0.0) | !(x_n == x_n) |
                                (x_n <= 0 && x > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)) |
-                               (x < 0 && x_n >= 0) | (down && x_n < 0 && !inj) |
-                               (P.feb_dn > 0 && x_n > P.feb_dn) | (x_n > 1.1 * prp_x) |
-                               (x_n >= P.x_grid_stop && (x < P.x_grid_stop || (x < prp_x && x_n >= prp_x) || ELECTRON));
+                               (x < 0 && x_n >= 0) | (P.feb_dn > 0 && x_n > P.feb_dn);
+                        double prp_n = prp_x;
+                        if (x_n > 1.1 * prp_x) {
+                            // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes only beyond 6.91 L_diff
+                            double v_fac;
+                            if (ELECTRON && ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * gd) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
+                            else v_fac = grt * ptot / (P.m * gam_pf * P.u2);
+                            park |= x_n > 6.91 * (P.eta_mfp / 3 * v_fac);
+                        }
+                        if (x_n >= P.x_grid_stop) {
+                            if (x < P.x_grid_stop) {
+                                // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP (custom eps_B is never here)
+                                const double g2 = ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
+                                prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2));
+                            } else {
+                                park |= (x < prp_x && x_n >= prp_x) | ELECTRON;  // PRP crossing: probability-of-return test
+                            }
+                        }
+#ifdef MCS_PARK_REASONS
+                        if (park) {
+                            int why = (x < 0 && x_n >= 0) ? 8 :
+                                      (x_n >= P.x_grid_stop && x < P.x_grid_stop) ? 10 : (x < prp_x && x_n >= prp_x) ? 11 :
+                                      (x_n > 1.1 * prp_x) ? 12 : (x_n <= 0 && x > 0 && !inj) ? 13 : 14;
+                            count(P, CNT_PARK0 + why);
+                        }
+#endif
                         if (!park) {
                             // zone search (all_flux.jl:65-82) and the crossing event
                             const bool dn = x_n > x;
@@ -1163,9 +1193,11 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                                 if (dn) { int k = i_grid + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig = k - 1; }
                                 else { int k = i_grid; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig = k; }
                             }
+                            if (down && x_n < 0) inj = true;  // particle_loop.jl:433-435 (before all_flux)
                             const bool feb_x = inj && x_n < P.feb_up && x >= P.feb_up;
                             if (ig != i_grid || (feb_x && ig <= P.i_grid_feb))
                                 fev = EV_VALID | (inj ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
+                            prp_x = prp_n;
                             helix++; c_fast_lane++;
                             acct = acct_n; gper = gper_n; t_step = t_n; xsel = xsel_n;
                             pb = pb_n; pperp = pperp_n; phi = phi_n;
