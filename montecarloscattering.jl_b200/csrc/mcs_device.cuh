@@ -1097,13 +1097,24 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                     bool park = (helix >= P.helix_cap) | (i_return == 1) | (xsel > 1) |
                                 (P.energy_transfer_frac > 0 && !inj && x_old_le0 && i_grid_old != i_grid) |
                                 (ptot > P.pmax_cutoff) | (inj && x < P.feb_up) | (P.age_max > 0 && acct > P.age_max);
-                    if (i_grid != iz) {
-                        // Code Block 3 zone change: stays here unless the flow speed differs (then transform_p_PSP: general pass)
-                        if (P.ux[i_grid] != ux) park = true;
-                        else if (!park) {
-                            iz = i_grid;
-                            gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
-                            gd = 1 / (P.zz * P.bt[iz]);
+                    if (i_grid != iz && !park) {
+                        // Code Block 3 zone change (particle_loop.jl:186-228); the boost is an out-of-line call
+                        const int iz_old = iz;
+                        iz = i_grid;
+                        const double ux_n = P.ux[iz];
+                        gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                        gd = 1 / (P.zz * P.bt[iz]);
+                        if (ux_n != ux) {
+                            ux = ux_n;
+                            Mom mi;
+                            mi.ptot = ptot; mi.pb = pb; mi.pperp = pperp; mi.gam_pf = gam_pf; mi.phi = phi;
+                            const Mom mo = transform_p_PSP(P, iz_old, iz, mi);
+                            ptot = mo.ptot; pb = mo.pb; pperp = mo.pperp; gam_pf = mo.gam_pf; phi = mo.phi;
+                            gr = pperp * P.c * gd;
+                            grt = ptot * P.c * gd;
+                            inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
+                            // the boosted momentum may now exceed a cut-off: let the general pass decide
+                            park = (ptot > P.pmax_cutoff) | (down && ptot > P.pcut);
                         }
                     }
                     double acct_n = acct;
@@ -1158,9 +1169,14 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         // anything the general pass would have to act on after the move -> nothing is committed
                         park = !(sd2 >= 0.0) | !(sn2 > 0.0) | !(x_n == x_n) |
                                (x_n <= 0 && x > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)) |
-                               (x < 0 && x_n >= 0) | (P.feb_dn > 0 && x_n > P.feb_dn);
+                               (P.feb_dn > 0 && x_n > P.feb_dn);
                         double prp_n = prp_x;
-                        if (x_n > 1.1 * prp_x) {
+                        const bool cross_down = x < 0 && x_n >= 0;
+                        if (cross_down) {  // particle_loop.jl:413-429: first/next arrival downstream, make the region long enough
+                            const double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
+                            prp_n = fmax(prp_x, L);
+                        }
+                        if (x_n > 1.1 * prp_n) {
                             // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes only beyond 6.91 L_diff
                             double v_fac;
                             if (ELECTRON && ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * gd) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
@@ -1173,7 +1189,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                                 const double g2 = ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
                                 prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2));
                             } else {
-                                park |= (x < prp_x && x_n >= prp_x) | ELECTRON;  // PRP crossing: probability-of-return test
+                                park |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
                             }
                         }
 #ifdef MCS_PARK_REASONS
@@ -1193,6 +1209,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                                 if (dn) { int k = i_grid + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig = k - 1; }
                                 else { int k = i_grid; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig = k; }
                             }
+                            if (cross_down) down = true;
                             if (down && x_n < 0) inj = true;  // particle_loop.jl:433-435 (before all_flux)
                             const bool feb_x = inj && x_n < P.feb_up && x >= P.feb_up;
                             if (ig != i_grid || (feb_x && ig <= P.i_grid_feb))
