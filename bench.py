@@ -252,6 +252,15 @@ def main():
     dev_s = allmax(tm["ion_loop_ms"]) * 1e-3
     wall_s = allmax(wall)
     kern_s = allmax(tm["transport_ms"]) * 1e-3
+    per_rank_kernel_ms = per_rank_steps = per_rank_particles = None
+    if dist is not None:
+        g = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor([tm["transport_ms"]], dtype=torch.float64, device="cuda"))
+        per_rank_kernel_ms = [round(float(x.item()) / a.steps, 1) for x in g]
+        dist.all_gather(g, torch.tensor([float(tm["local_steps"])], dtype=torch.float64, device="cuda"))
+        per_rank_steps = [float(x.item()) / a.steps for x in g]
+        dist.all_gather(g, torch.tensor([float(tm["local_particles"])], dtype=torch.float64, device="cuda"))
+        per_rank_particles = [float(x.item()) / a.steps for x in g]
     value = steps_per_iter * a.steps / dev_s
     e2e = steps_per_iter * a.steps / wall_s
     # dominant kernel: this rank's steps over this rank's kernel time
@@ -269,7 +278,8 @@ def main():
                 "s_per_iteration_device": dev_s / a.steps, "s_per_iteration_e2e": wall_s / a.steps}),
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": wall_s / a.steps * 1e3},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "per_rank_kernel_ms_per_step": per_rank_kernel_ms,
+            "per_rank_steps_per_step": per_rank_steps, "per_rank_particles_per_step": per_rank_particles,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "transport_kernel<false>", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,

@@ -186,6 +186,7 @@ typedef struct McsTiming {
     double split_ms, reduce_ms, h2d_ms, d2h_ms, comm_ms;
     double ion_loop_ms;  /* device time of whole mcs_run_ion calls (transport + split + counts + comm) */
     int64_t transport_launches, other_launches;
+    int64_t local_steps, local_particles; /* this rank's scattering steps / particles entered into pcuts (before any all-reduce) */
 } McsTiming;
 
 typedef struct McsHandle McsHandle;

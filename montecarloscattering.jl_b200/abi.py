@@ -92,7 +92,7 @@ class McsTraceRec(C.Structure):
 class McsTiming(C.Structure):
     _fields_ = [
         ("transport_ms", _d), ("split_ms", _d), ("reduce_ms", _d), ("h2d_ms", _d), ("d2h_ms", _d), ("comm_ms", _d), ("ion_loop_ms", _d),
-        ("transport_launches", _i64), ("other_launches", _i64),
+        ("transport_launches", _i64), ("other_launches", _i64), ("local_steps", _i64), ("local_particles", _i64),
     ]
 
 

@@ -133,6 +133,8 @@ struct McsHandle {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     long long* d_gather = nullptr;
+    unsigned char* d_xchg = nullptr;  // all-gather buffer of saved records for the rebalancing split
+    size_t xchg_bytes = 0;
     McsTiming tm;
     DevParams P;
 };
@@ -164,7 +166,7 @@ extern "C" int mcs_destroy(McsHandle* h) {
     cudaFree(h->d_saved_idx); cudaFree(h->d_block_off); cudaFree(h->d_total); cudaFree(h->d_block_cnt);
     cudaFree(h->d_tally); cudaFree(h->d_u64); cudaFree(h->d_tg); cudaFree(h->d_tpx); cudaFree(h->d_tpt); cudaFree(h->d_tw);
     cudaFree(h->d_partials); cudaFree(h->d_replay_u); cudaFree(h->d_replay_off); cudaFree(h->d_trace_slot);
-    cudaFree(h->d_trace_recs); cudaFree(h->d_trace_cnt); cudaFree(h->d_gather);
+    cudaFree(h->d_trace_recs); cudaFree(h->d_trace_cnt); cudaFree(h->d_gather); cudaFree(h->d_xchg);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -458,10 +460,14 @@ extern "C" int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pc
         h->tm.transport_ms += ms;
     }
     h->n_saved_last = (long long)(h->h_counters[CNT_FATE0] - saved0);
+    h->tm.local_steps += (int64_t)(h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO] - steps0);
+    h->tm.local_particles += n;
     if (n_saved) *n_saved = h->n_saved_last;
     if (n_steps) *n_steps = (int64_t)(h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO] - steps0);
     return MCS_OK;
 }
+
+static int compact_saved(McsHandle* h);
 
 extern "C" int mcs_split_explicit(McsHandle* h, int64_t i_mult, int64_t first_global_child, int64_t* n_new_local) {
     if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
@@ -471,13 +477,11 @@ extern "C" int mcs_split_explicit(McsHandle* h, int64_t i_mult, int64_t first_gl
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev2, h->stream));
     if (ns > 0) {
-        const int nb = (int)((n + 1023) / 1024);
-        count_saved_kernel<<<nb, 1024, 0, h->stream>>>(h->d_l_save, n, h->d_block_cnt);
-        scan_blocks_kernel<<<1, 1024, 0, h->stream>>>(h->d_block_cnt, nb, h->d_block_off, h->d_total);
-        compact_saved_kernel<<<nb, 1024, 0, h->stream>>>(h->d_l_save, n, h->d_block_off, h->d_saved_idx);
+        int rc = compact_saved(h);
+        if (rc) return rc;
         clone_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, h->stream>>>(h->pop[1], h->pop[h->nxt], h->d_saved_idx, n_out, i_mult);
         CU(cudaGetLastError());
-        h->tm.other_launches += 4;
+        h->tm.other_launches++;
     }
     CU(cudaEventRecord(h->ev3, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -490,34 +494,89 @@ extern "C" int mcs_split_explicit(McsHandle* h, int64_t i_mult, int64_t first_gl
     return MCS_OK;
 }
 
+// Local part of new_pcut: order-preserving list of the saved indices (h->d_saved_idx[0..ns))
+static int compact_saved(McsHandle* h) {
+    const long long n = h->n_use;
+    if (h->n_saved_last > 0) {
+        const int nb = (int)((n + 1023) / 1024);
+        count_saved_kernel<<<nb, 1024, 0, h->stream>>>(h->d_l_save, n, h->d_block_cnt);
+        scan_blocks_kernel<<<1, 1024, 0, h->stream>>>(h->d_block_cnt, nb, h->d_block_off, h->d_total);
+        compact_saved_kernel<<<nb, 1024, 0, h->stream>>>(h->d_l_save, n, h->d_block_off, h->d_saved_idx);
+        CU(cudaGetLastError());
+        h->tm.other_launches += 3;
+    }
+    return MCS_OK;
+}
+
 extern "C" int mcs_split(McsHandle* h, int64_t n_pts_target, int64_t* n_new_local, int64_t* n_new_global, int64_t* i_mult_out) {
     if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
-    long long ns_global = h->n_saved_last, lower = 0;
-    if (h->nranks > 1) {  // one all-gather of the per-rank n_saved
-        CU(cudaSetDevice(h->device));
-        long long v = h->n_saved_last;
-        long long all[64];
-        CU(cudaEventRecord(h->ev2, h->stream));
-        CU(cudaMemcpyAsync(h->d_gather + h->rank, &v, 8, cudaMemcpyHostToDevice, h->stream));
-        NC(g_nccl.AllGather(h->d_gather + h->rank, h->d_gather, 1, ncclInt64, h->comm, h->stream));
-        CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 8, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaEventRecord(h->ev3, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
-        h->tm.comm_ms += ms;
-        ns_global = 0;
-        for (int r = 0; r < h->nranks; r++) { ns_global += all[r]; if (r < h->rank) lower += all[r]; }
+    if (h->nranks == 1) {
+        const long long ns = h->n_saved_last;
+        h->n_saved_global_last = ns;
+        if (ns <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
+        long long i_mult = n_pts_target / ns;  // cuts.jl:42
+        if (i_mult < 1) i_mult = 1;
+        int64_t k = 0;
+        int rc = mcs_split_explicit(h, i_mult, 0, &k);
+        if (rc) return rc;
+        if (n_new_local) *n_new_local = k;
+        if (n_new_global) *n_new_global = k;
+        if (i_mult_out) *i_mult_out = i_mult;
+        return MCS_OK;
     }
-    h->n_saved_global_last = ns_global;
-    if (ns_global <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
-    long long i_mult = n_pts_target / ns_global;  // cuts.jl:42
+    // ---- multi-GPU: all-gather the saved records, every rank clones an equal slice of the global child range ----
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev2, h->stream));
+    long long v = h->n_saved_last, all[64];
+    CU(cudaMemcpyAsync(h->d_gather + h->rank, &v, 8, cudaMemcpyHostToDevice, h->stream));
+    NC(g_nccl.AllGather(h->d_gather + h->rank, h->d_gather, 1, ncclInt64, h->comm, h->stream));
+    CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    GatherPrefix pre;
+    memset(&pre, 0, sizeof pre);
+    pre.nranks = h->nranks;
+    long long S = 0, max_ns = 0;
+    for (int r = 0; r < h->nranks; r++) { pre.start[r] = S; S += all[r]; if (all[r] > max_ns) max_ns = all[r]; }
+    pre.start[h->nranks] = S;
+    h->n_saved_global_last = S;
+    if (S <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
+    long long i_mult = n_pts_target / S;  // cuts.jl:42 on the GLOBAL count
     if (i_mult < 1) i_mult = 1;
-    int64_t k = 0;
-    int rc = mcs_split_explicit(h, i_mult, i_mult * lower, &k);
+    const long long C = S * i_mult;
+    const long long c0 = C * h->rank / h->nranks, c1 = C * (h->rank + 1) / h->nranks, n_out = c1 - c0;
+    if (n_out > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "split population exceeds n_pts_max");
+    const long long stride = (max_ns + 15) / 16 * 16;
+    const size_t need = (size_t)stride * 82 * (size_t)h->nranks;
+    if (need > h->xchg_bytes) {
+        cudaFree(h->d_xchg); h->d_xchg = nullptr; h->xchg_bytes = 0;
+        CU(cudaMalloc(&h->d_xchg, need + need / 4));
+        h->xchg_bytes = need + need / 4;
+    }
+    int rc = compact_saved(h);
     if (rc) return rc;
-    if (n_new_local) *n_new_local = k;
-    if (n_new_global) *n_new_global = ns_global * i_mult;
+    unsigned char* mine = h->d_xchg + (size_t)h->rank * (size_t)stride * 82;
+    if (h->n_saved_last > 0) {
+        pack_saved_kernel<<<(unsigned)((h->n_saved_last + 255) / 256), 256, 0, h->stream>>>(h->pop[1], h->d_saved_idx, h->n_saved_last,
+                                                                                        mine, stride);
+        CU(cudaGetLastError());
+        h->tm.other_launches++;
+    }
+    NC(g_nccl.AllGather(mine, h->d_xchg, (size_t)stride * 82, ncclUint8, h->comm, h->stream));
+    if (n_out > 0) {
+        clone_gathered_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, h->stream>>>(h->d_xchg, stride, pre, h->pop[h->nxt], c0, n_out,
+                                                                                   i_mult);
+        CU(cudaGetLastError());
+        h->tm.other_launches++;
+    }
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    h->tm.split_ms += ms;
+    int t = h->cur; h->cur = h->nxt; h->nxt = t;
+    h->n_use = n_out; h->first_global = c0;
+    if (n_new_local) *n_new_local = n_out;
+    if (n_new_global) *n_new_global = C;
     if (i_mult_out) *i_mult_out = i_mult;
     return MCS_OK;
 }

@@ -1359,6 +1359,50 @@ __global__ void clone_kernel(PopPtrs src, PopPtrs dst, const long long* __restri
     dst.acctime[o] = src.acctime[j]; dst.phi[o] = src.phi[j]; dst.tcut[o] = src.tcut[j];
 }
 
+// Multi-GPU split with rebalancing: every rank packs its saved records (SoA, padded to `stride` records) into its block of
+// a gather buffer; after ncclAllGather each rank clones an equal contiguous slice of the GLOBAL child index range.
+// Block layout (bytes): 8 f64 arrays | 2 i64 arrays | 2 u8 arrays, each `stride` long -> 82 * stride bytes.
+struct GatherPrefix { long long start[65]; int nranks; };
+
+__device__ __forceinline__ unsigned char* gather_block(unsigned char* buf, int q, long long stride) {
+    return buf + (size_t)q * (size_t)stride * 82;
+}
+
+__global__ void pack_saved_kernel(PopPtrs src, const long long* __restrict__ saved_idx, long long ns, unsigned char* block,
+                                  long long stride) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ns) return;
+    const long long j = saved_idx[r];
+    double* f = reinterpret_cast<double*>(block);
+    f[r] = src.weight[j]; f[stride + r] = src.ptot[j]; f[2 * stride + r] = src.pb[j]; f[3 * stride + r] = src.x[j];
+    f[4 * stride + r] = src.xn_per[j]; f[5 * stride + r] = src.prp_x[j]; f[6 * stride + r] = src.acctime[j];
+    f[7 * stride + r] = src.phi[j];
+    long long* g = reinterpret_cast<long long*>(block + (size_t)stride * 64);
+    g[r] = src.grid[j]; g[stride + r] = src.tcut[j];
+    uint8_t* b = block + (size_t)stride * 80;
+    b[r] = src.down[j]; b[stride + r] = src.inj[j];
+}
+
+__global__ void clone_gathered_kernel(unsigned char* buf, long long stride, GatherPrefix pre, PopPtrs dst, long long c0,
+                                      long long n_out, long long i_mult) {
+    long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    const long long sidx = (c0 + o) / i_mult;  // global rank of the saved parent (cuts.jl:69-91 order)
+    int q = 0;
+    while (q + 1 < pre.nranks && sidx >= pre.start[q + 1]) q++;
+    const long long r = sidx - pre.start[q];
+    const unsigned char* block = gather_block(buf, q, stride);
+    const double* f = reinterpret_cast<const double*>(block);
+    dst.weight[o] = f[r] / (double)i_mult;  // cuts.jl:77
+    dst.ptot[o] = f[stride + r]; dst.pb[o] = f[2 * stride + r]; dst.x[o] = f[3 * stride + r];
+    dst.xn_per[o] = f[4 * stride + r]; dst.prp_x[o] = f[5 * stride + r]; dst.acctime[o] = f[6 * stride + r];
+    dst.phi[o] = f[7 * stride + r];
+    const long long* g = reinterpret_cast<const long long*>(block + (size_t)stride * 64);
+    dst.grid[o] = g[r]; dst.tcut[o] = g[stride + r];
+    const uint8_t* b = block + (size_t)stride * 80;
+    dst.down[o] = b[r]; dst.inj[o] = b[stride + r];
+}
+
 __global__ void fill_defaults_kernel(PopPtrs p, long long n, int has_down, int has_inj, int has_xn, int has_prp,
                                      int has_acc, int has_tcut, double xn_fine, double x_grid_stop) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
