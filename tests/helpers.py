@@ -15,6 +15,15 @@ def small_inputs():
         "relativistic": problem.relativistic_input(600, momentum_cutoffs=problem.DEFAULT_PCUTS[:9]),
         "nonlinear": problem.nonlinear_input(800, momentum_cutoffs=LADDER[:5], num_iterations=1),
         "multi": problem.multi_species_input(500, momentum_cutoffs=problem.DEFAULT_PCUTS[:6]),
+        # feature coverage beyond the five headline configs (each switches on one more branch of particle_loop)
+        "tcuts_age": problem.planar_test_particle_input(800, momentum_cutoffs=LADDER[:4], maximum_age=3.0e4,
+                                                        tcuts=[1e2, 3e2, 1e3, 3e3, 1e4, 1e6]),
+        "xspec": problem.planar_test_particle_input(600, momentum_cutoffs=LADDER[:3], x_spec=[-0.5, -0.05, 0.2, 3.0]),
+        "injfrac": problem.planar_test_particle_input(800, momentum_cutoffs=LADDER[:4], inj_fracs=[0.3]),
+        "feb_down": problem.planar_test_particle_input(800, momentum_cutoffs=LADDER[:4], feb_downstream=(4.0, 0.0)),
+        "bundled_scatter": problem.ShockInput(no_scatter=False, no_dsa=False, n_pts_inj=300, n_pts_pcut=400, n_pts_pcut_hi=400,
+                                              momentum_cutoffs=problem.DEFAULT_PCUTS[:6]),
+        "no_retro_error": problem.planar_test_particle_input(300, momentum_cutoffs=LADDER[:2], use_retro=False),
     }
 
 

@@ -30,7 +30,8 @@ def _ion_for(name, run):
     return 3 if name == "multi" else 1
 
 
-@pytest.mark.parametrize("name", ["bundled", "planar", "relativistic", "nonlinear", "multi"])
+@pytest.mark.parametrize("name", ["bundled", "planar", "relativistic", "nonlinear", "multi", "tcuts_age", "xspec", "injfrac",
+                                  "feb_down", "bundled_scatter", "no_retro_error"])
 def test_per_particle_parity(olib, clib, name):
     inp = small_inputs()[name]
     run = problem.setup_run(inp)
@@ -69,7 +70,8 @@ def test_per_particle_parity(olib, clib, name):
         assert to.stats == tc.stats
         assert np.array_equal(to.num_crossings, tc.num_crossings)
         for nm in ("pxx_flux", "pxz_flux", "energy_flux", "esc_psd_feb_upstream", "esc_psd_feb_downstream",
-                   "esc_energy_eff", "esc_num_eff", "weight_coupled", "spectra_coupled", "energy_transfer_pool"):
+                   "esc_energy_eff", "esc_num_eff", "weight_coupled", "spectra_coupled", "energy_transfer_pool",
+                   "spectra_sf", "spectra_pf"):
             x, y = getattr(to, nm), getattr(tc, nm)
             assert np.array_equal(x != 0, y != 0), nm
             assert rel_close(x, y, 0, atol_frac=1e-6) <= TOL_TALLY, nm
