@@ -111,6 +111,8 @@ typedef struct McsConfig {
     uint32_t compat;
     int32_t rng_mode;
     int32_t threads;    /* CPU oracle only: OpenMP threads (0/1 = serial, ordered) */
+    int32_t bin_thermal; /* also bin every thermal crossing on the fly (McsTallies.therm_d2N_*) so that the
+                            unbounded crossing log is not needed: 0 = off, 1 = on */
     int32_t dynamic_queue; /* 0 = particles dealt to warps in a fixed interleaved order (run-to-run deterministic tallies);
                               1 = global atomic work queue (load-balanced, summation order varies) */
 } McsConfig;
@@ -147,6 +149,11 @@ typedef struct McsTallies {
     double* energy_transfer_pool;   /* [n_grid] donated this ion   particle_loop.jl:681  */
     double* spectra_sf;             /* [(psd_max+1)*n_xspec]              all_flux.jl:178 */
     double* spectra_pf;             /* [(psd_max+1)*n_xspec]              all_flux.jl:185 */
+    /* SURVEY 8(f1) — device-side forms of what the host consumers build from the tallies; index = jth + (T+2)*(k + (M+2)*(i-1)),
+     * i.e. the reference's [jth, k, i] order restricted to the bins in use.  Filled only with cfg.bin_thermal = 1. */
+    double* therm_d2N_sf;           /* thermal crossings binned in the shock frame     particle_counter.jl:426-445 */
+    double* therm_d2N_pf;           /* ... boosted to the local plasma frame first     thermo_calcs.jl:133-164     */
+    double* dNdp_cr_sf;             /* [(M+2)*n_grid]: sum over angle of psd           particle_counter.jl:81-85   */
     /* scalars (out) */
     double esc_flux, px_esc_feb, energy_esc_feb;       /* particle_finish.jl:81,91,92  */
     double sum_P_downstream, sum_KE_downstream;        /* particle_loop.jl:485-486     */

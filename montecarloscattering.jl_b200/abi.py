@@ -50,7 +50,7 @@ class McsConfig(C.Structure):
         ("do_rad_losses", _i32), ("do_retro", _i32), ("do_tcuts", _i32), ("dont_DSA", _i32),
         ("dont_scatter", _i32), ("use_custom_frg", _i32), ("use_custom_epsB", _i32),
         ("helix_cap", _i32), ("retro_cap", _i64), ("seed", _u64), ("compat", _u32),
-        ("rng_mode", _i32), ("threads", _i32), ("dynamic_queue", _i32),
+        ("rng_mode", _i32), ("threads", _i32), ("bin_thermal", _i32), ("dynamic_queue", _i32),
     ]
 
 
@@ -66,6 +66,7 @@ class McsTallies(C.Structure):
         ("esc_psd_feb_upstream", _pd), ("esc_psd_feb_downstream", _pd),
         ("esc_energy_eff", _pd), ("esc_num_eff", _pd), ("weight_coupled", _pd), ("spectra_coupled", _pd),
         ("energy_transfer_pool", _pd), ("spectra_sf", _pd), ("spectra_pf", _pd),
+        ("therm_d2N_sf", _pd), ("therm_d2N_pf", _pd), ("dNdp_cr_sf", _pd),
         ("esc_flux", _d), ("px_esc_feb", _d), ("energy_esc_feb", _d),
         ("sum_P_downstream", _d), ("sum_KE_downstream", _d),
         ("px_esc_upstream", _d), ("energy_esc_upstream", _d),
@@ -185,6 +186,9 @@ class Tallies:
     energy_transfer_pool: np.ndarray
     spectra_sf: np.ndarray
     spectra_pf: np.ndarray
+    therm_d2N_sf: np.ndarray = None  # [n_grid, M+2, T+2] (C order of the reference's [jth, k, i])
+    therm_d2N_pf: np.ndarray = None
+    dNdp_cr_sf: np.ndarray = None    # [n_grid, M+2]
     scalars: dict = field(default_factory=dict)
     stats: dict = field(default_factory=dict)
 
@@ -309,13 +313,16 @@ class Engine:
             esc_energy_eff=z(e1), esc_num_eff=z(e1), weight_coupled=z(NA_C), spectra_coupled=z((NA_C, e1)),
             energy_transfer_pool=z(ng), spectra_sf=z((max(nx, 1), e1)), spectra_pf=z((max(nx, 1), e1)),
         )
+        if self.cfg.bin_thermal:
+            t.therm_d2N_sf, t.therm_d2N_pf, t.dNdp_cr_sf = z((ng, M2, T2)), z((ng, M2, T2)), z((ng, M2))
         st = McsTallies()
         for nm, typ in (("pxx_flux", _pd), ("pxz_flux", _pd), ("energy_flux", _pd), ("psd", _pd),
                         ("num_crossings", _pi64), ("therm_grid", _pi64), ("therm_px_sk", _pd),
                         ("therm_ptot_sk", _pd), ("therm_weight", _pd), ("esc_psd_feb_upstream", _pd),
                         ("esc_psd_feb_downstream", _pd), ("esc_energy_eff", _pd), ("esc_num_eff", _pd),
                         ("weight_coupled", _pd), ("spectra_coupled", _pd), ("energy_transfer_pool", _pd),
-                        ("spectra_sf", _pd), ("spectra_pf", _pd)):
+                        ("spectra_sf", _pd), ("spectra_pf", _pd), ("therm_d2N_sf", _pd), ("therm_d2N_pf", _pd),
+                        ("dNdp_cr_sf", _pd)):
             setattr(st, nm, _ptr(getattr(t, nm), typ))
         self._check(self.lib.mcs_end_ion(self._h, C.byref(st)))
         if want_log:

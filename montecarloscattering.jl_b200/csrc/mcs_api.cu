@@ -113,7 +113,8 @@ struct McsHandle {
     // tallies: one packed FP64 buffer (single all-reduce) + one packed u64 buffer
     double* d_tally = nullptr;
     size_t n_tally = 0, off_pxx = 0, off_pxz = 0, off_efl = 0, off_psd = 0, off_esc_up = 0, off_esc_dn = 0, off_en_eff = 0,
-           off_num_eff = 0, off_wc = 0, off_sc = 0, off_pool = 0, off_sf = 0, off_pf = 0, off_scal = 0;
+           off_num_eff = 0, off_wc = 0, off_sc = 0, off_pool = 0, off_sf = 0, off_pf = 0, off_scal = 0, off_thsf = 0, off_thpf = 0,
+           off_dndp = 0;
     unsigned long long* d_u64 = nullptr;  // [ng crossings | CNT_N counters]
     unsigned long long h_counters[CNT_N];
     long long *d_tg = nullptr;
@@ -238,6 +239,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     h->off_esc_up = take((size_t)E1 * E1); h->off_esc_dn = take((size_t)E1 * E1); h->off_en_eff = take(E1);
     h->off_num_eff = take(E1); h->off_wc = take(MCS_NA_C); h->off_sc = take((size_t)E1 * MCS_NA_C); h->off_pool = take(ng);
     h->off_sf = take((size_t)E1 * MCS_MAX_XSPEC); h->off_pf = take((size_t)E1 * MCS_MAX_XSPEC); h->off_scal = take(SC_N);
+    if (cfg->bin_thermal) { h->off_thsf = take(psd_len(h)); h->off_thpf = take(psd_len(h)); h->off_dndp = take((size_t)(h->M + 2) * ng); }
     h->n_tally = o;
     CUA(cudaMalloc(&h->d_tally, o * 8));
     CUA(cudaMalloc(&h->d_u64, (size_t)(ng + CNT_N) * 8));
@@ -295,6 +297,8 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     t.psd = b + h->off_psd; t.esc_up = b + h->off_esc_up; t.esc_dn = b + h->off_esc_dn; t.esc_en_eff = b + h->off_en_eff;
     t.esc_num_eff = b + h->off_num_eff; t.w_coupled = b + h->off_wc; t.s_coupled = b + h->off_sc; t.pool = b + h->off_pool;
     t.spec_sf = b + h->off_sf; t.spec_pf = b + h->off_pf;
+    t.therm_sf = cfg->bin_thermal ? b + h->off_thsf : nullptr; t.therm_pf = cfg->bin_thermal ? b + h->off_thpf : nullptr;
+    t.dndp_cr = cfg->bin_thermal ? b + h->off_dndp : nullptr;
     t.counters = h->d_u64 + ng;
     t.tg = h->d_tg; t.tpx = h->d_tpx; t.tpt = h->d_tpt; t.tw = h->d_tw; t.na_cr = cfg->na_cr;
     t.block_partials = h->d_partials;
@@ -659,6 +663,12 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     CU(cudaEventRecord(h->ev2, h->stream));
     const size_t ng = (size_t)h->ng;
     double* b = h->d_tally;
+    if (h->cfg.bin_thermal) {
+        const int M2 = h->M + 2, T2 = h->T + 2;
+        sum_angle_kernel<<<(M2 * h->ng + 255) / 256, 256, 0, h->stream>>>(b + h->off_psd, M2, T2, h->ng, b + h->off_dndp);
+        CU(cudaGetLastError());
+        h->tm.other_launches++;
+    }
 #define DN(dst, src, count) do { if (dst && (count) > 0) CU(cudaMemcpyAsync(dst, src, (size_t)(count) * 8, cudaMemcpyDeviceToHost, h->stream)); } while (0)
     DN(t->pxx_flux, b + h->off_pxx, ng); DN(t->pxz_flux, b + h->off_pxz, ng); DN(t->energy_flux, b + h->off_efl, ng);
     DN(t->psd, b + h->off_psd, psd_len(h)); DN(t->num_crossings, h->d_u64, ng);
@@ -669,6 +679,10 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     DN(t->weight_coupled, b + h->off_wc, MCS_NA_C); DN(t->spectra_coupled, b + h->off_sc, (size_t)E1 * MCS_NA_C);
     DN(t->energy_transfer_pool, b + h->off_pool, ng);
     DN(t->spectra_sf, b + h->off_sf, (size_t)E1 * h->cfg.n_xspec); DN(t->spectra_pf, b + h->off_pf, (size_t)E1 * h->cfg.n_xspec);
+    if (h->cfg.bin_thermal) {
+        DN(t->therm_d2N_sf, b + h->off_thsf, psd_len(h)); DN(t->therm_d2N_pf, b + h->off_thpf, psd_len(h));
+        DN(t->dNdp_cr_sf, b + h->off_dndp, (size_t)(h->M + 2) * ng);
+    }
     double sc[SC_N];
     CU(cudaMemcpyAsync(sc, b + h->off_scal, SC_N * 8, cudaMemcpyDeviceToHost, h->stream));
 #undef DN

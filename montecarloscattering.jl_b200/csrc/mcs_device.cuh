@@ -86,6 +86,9 @@ struct TallyPtrs {
     double* pool;           // [n_grid]
     double* spec_sf;        // [E1*MAX_XSPEC]
     double* spec_pf;
+    double* therm_sf;       // [(T+2)(M+2) n_grid] or null: thermal crossings binned in the shock frame
+    double* therm_pf;       // ... in the local plasma frame
+    double* dndp_cr;        // [(M+2) n_grid]
     unsigned long long* counters;  // [CNT_N]
     long long* tg;          // thermal-crossing log
     double *tpx, *tpt, *tw;
@@ -571,6 +574,23 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
                     else over++;
                 }
                 if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
+            }
+        }
+        if (P.t.therm_sf != nullptr && nrec > 0) {
+            // what get_dNdp_2D (particle_counter.jl:426-445) and thermo_calcs (thermo_calcs.jl:133-164) build
+            // from the crossing log, accumulated on the fly so the log can stay small
+            const double w = weight * (ptot_sk > fabs(sx * SPIKE_AWAY) ? fabs(SPIKE_AWAY / ux) : fabs(gam_sk * P.aa * P.mp / sx));
+            const size_t sT = (size_t)(P.T + 2), sM = (size_t)(P.M + 2);
+            const int k = psd_bin_momentum(P, ptot_sk), jt = psd_bin_angle(P, sx, ptot_sk);
+            const double E0 = P.m * (P.c * P.c), etot = hypot(ptot_sk * P.c, E0);
+            for (int i = lo; i <= hi; i++) {
+                red_add_f64(&P.t.therm_sf[(size_t)jt + sT * ((size_t)k + sM * (size_t)(i - 1))], w);
+                const double g = P.gsf[i], b = P.ux[i] / P.c;
+                double pxX = g * (sx - b * etot / P.c);
+                const double ptX = sqrt((ptot_sk * ptot_sk - sx * sx) + pxX * pxX);
+                if (fabs(pxX) > ptX) pxX = copysign(ptX, pxX);
+                const int kX = psd_bin_momentum(P, ptX), jX = psd_bin_angle(P, pxX, ptX);
+                red_add_f64(&P.t.therm_pf[(size_t)jX + sT * ((size_t)kX + sM * (size_t)(i - 1))], w);
             }
         }
     }
@@ -1401,6 +1421,19 @@ __global__ void clone_gathered_kernel(unsigned char* buf, long long stride, Gath
     dst.grid[o] = g[r]; dst.tcut[o] = g[stride + r];
     const uint8_t* b = block + (size_t)stride * 80;
     dst.down[o] = b[r]; dst.inj[o] = b[stride + r];
+}
+
+// particle_counter.jl:81-85: shock-frame dN(p) of the cosmic rays = sum of the PSD over the angle bins
+__global__ void sum_angle_kernel(const double* __restrict__ psd, int M2, int T2, int ng, double* dndp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;  // k + M2 * i
+    if (idx >= M2 * ng) return;
+    const int k = idx % M2, i = idx / M2;
+    double s = 0.0;
+    for (int j = 0; j < T2; j++) {
+        double v = psd[(size_t)k + (size_t)M2 * ((size_t)j + (size_t)T2 * (size_t)i)];
+        if (v > 0) s += v;
+    }
+    dndp[idx] = s;
 }
 
 __global__ void fill_defaults_kernel(PopPtrs p, long long n, int has_down, int has_inj, int has_xn, int has_prp,

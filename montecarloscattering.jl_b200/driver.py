@@ -18,7 +18,7 @@ from . import abi, problem
 
 def make_config(lib, run: problem.Run, *, n_pts_cap: int | None = None, seed: int = 210, na_cr: int | None = None,
                 rng_mode: int = abi.RNG_PHILOX, compat: int = abi.COMPAT_DEFAULT, threads: int = 1,
-                device: int = -1, helix_cap: int = 10_000) -> abi.McsConfig:
+                device: int = -1, helix_cap: int = 10_000, bin_thermal: bool = False) -> abi.McsConfig:
     """Scalars of particle_loop's argument list (particle_loop.jl:1-31) as one POD struct."""
     inp = run.inp
     c = abi.default_config(lib)
@@ -52,6 +52,7 @@ def make_config(lib, run: problem.Run, *, n_pts_cap: int | None = None, seed: in
     c.dont_DSA, c.dont_scatter = int(inp.no_dsa), int(inp.no_scatter)
     c.use_custom_frg, c.use_custom_epsB = int(inp.use_custom_frg), int(inp.use_custom_epsB)
     c.helix_cap, c.seed, c.compat, c.rng_mode, c.threads = helix_cap, seed, compat, rng_mode, threads
+    c.bin_thermal = int(bin_thermal)
     return c
 
 

@@ -99,6 +99,7 @@ struct McsHandle {
     int64_t* tg;
     double *tpx, *tpt, *tw;
     double *esc_up, *esc_dn, *esc_en_eff, *esc_num_eff, *w_coupled, *s_coupled, *pool, *spec_sf, *spec_pf;
+    double *th_sf, *th_pf; /* thermal crossings binned on the fly, [jth + (T+2)*(k + (M+2)*(i-1))] */
     double esc_flux, px_esc_feb, en_esc_feb, sumP, sumKE, px_esc_up, en_esc_up;
     int64_t n_helix, n_retro, w_pperp, w_psdmom, n_negsqrt, n_retro_cap, n_err, n_fate[6];
     /* replay + trace */
@@ -401,6 +402,19 @@ static int all_flux(struct McsHandle* h, double aa, double pb_pf, double p_perp,
             }
             if (slot >= 0) {
                 h->tg[slot] = i; h->tpx[slot] = psk[0]; h->tpt[slot] = ptot_sk; h->tw[slot] = weight * abs_inv_vx;
+            }
+            if (c->bin_thermal) {
+                /* particle_counter.jl:426-445: shock-frame bins of the crossing */
+                int k = get_psd_bin_momentum(h, ptot_sk), jt = get_psd_bin_angle(h, psk[0], ptot_sk);
+                TADD(h, h->th_sf[(size_t)jt + (size_t)(h->T + 2) * ((size_t)k + (size_t)(h->M + 2) * (size_t)(i - 1))], weight * abs_inv_vx);
+                /* thermo_calcs.jl:133-164: boost to the plasma frame of zone i, then bin */
+                double E0 = m * (c->c_cms * c->c_cms), g = h->gsf[i], b = h->ux[i] / c->c_cms;
+                double etot = hypot(ptot_sk * c->c_cms, E0);
+                double pxX = g * (psk[0] - b * etot / c->c_cms);
+                double ptX = sqrt((ptot_sk * ptot_sk - psk[0] * psk[0]) + pxX * pxX);
+                if (fabs(pxX) > ptX) pxX = copysign(ptX, pxX);
+                int kX = get_psd_bin_momentum(h, ptX), jX = get_psd_bin_angle(h, pxX, ptX);
+                TADD(h, h->th_pf[(size_t)jX + (size_t)(h->T + 2) * ((size_t)kX + (size_t)(h->M + 2) * (size_t)(i - 1))], weight * abs_inv_vx);
             }
             TADD(h, h->ncross[i - 1], 1);
         }
@@ -838,6 +852,7 @@ int mcs_create(const McsConfig* cfg, McsHandle** out) {
     h->esc_up = calloc(e2, 8); h->esc_dn = calloc(e2, 8); h->esc_en_eff = calloc(e1, 8); h->esc_num_eff = calloc(e1, 8);
     h->w_coupled = calloc(MCS_NA_C, 8); h->s_coupled = calloc(e1 * MCS_NA_C, 8); h->pool = calloc(ng, 8);
     h->spec_sf = calloc(e1 * MCS_MAX_XSPEC, 8); h->spec_pf = calloc(e1 * MCS_MAX_XSPEC, 8);
+    h->th_sf = calloc(cfg->bin_thermal ? psd_len(h) : 1, 8); h->th_pf = calloc(cfg->bin_thermal ? psd_len(h) : 1, 8);
     if (bad || !h->xg || !h->psd || !h->tg || !h->tw || !h->l_save || !h->draws || !h->spec_pf) {
         mcs_destroy(h);
         return fail(MCS_ERR_NOMEM, "allocation failed");
@@ -855,7 +870,7 @@ int mcs_destroy(McsHandle* h) {
     free(h->pxx); free(h->pxz); free(h->efl); free(h->psd); free(h->ncross);
     free(h->tg); free(h->tpx); free(h->tpt); free(h->tw);
     free(h->esc_up); free(h->esc_dn); free(h->esc_en_eff); free(h->esc_num_eff); free(h->w_coupled);
-    free(h->s_coupled); free(h->pool); free(h->spec_sf); free(h->spec_pf);
+    free(h->s_coupled); free(h->pool); free(h->spec_sf); free(h->spec_pf); free(h->th_sf); free(h->th_pf);
     free(h->replay_u); free(h->replay_off); free(h->trace_idx); free(h->trace_recs); free(h->trace_cnt);
     free(h);
     return MCS_OK;
@@ -890,6 +905,7 @@ static void zero_ion_tallies(struct McsHandle* h) {
     memset(h->esc_num_eff, 0, e1 * 8); memset(h->w_coupled, 0, MCS_NA_C * 8);
     memset(h->s_coupled, 0, e1 * MCS_NA_C * 8); memset(h->pool, 0, ng * 8);
     memset(h->spec_sf, 0, e1 * MCS_MAX_XSPEC * 8); memset(h->spec_pf, 0, e1 * MCS_MAX_XSPEC * 8);
+    if (h->cfg.bin_thermal) { memset(h->th_sf, 0, psd_len(h) * 8); memset(h->th_pf, 0, psd_len(h) * 8); }
     h->esc_flux = h->px_esc_feb = h->en_esc_feb = h->sumP = h->sumKE = h->px_esc_up = h->en_esc_up = 0.0;
     h->n_helix = h->n_retro = h->w_pperp = h->w_psdmom = h->n_negsqrt = h->n_retro_cap = h->n_err = 0;
     memset(h->n_fate, 0, sizeof h->n_fate);
@@ -1019,6 +1035,20 @@ int mcs_end_ion(McsHandle* h, McsTallies* t) {
     CPY(t->weight_coupled, h->w_coupled, MCS_NA_C); CPY(t->spectra_coupled, h->s_coupled, e1 * MCS_NA_C);
     CPY(t->energy_transfer_pool, h->pool, ng);
     CPY(t->spectra_sf, h->spec_sf, e1 * (size_t)h->cfg.n_xspec); CPY(t->spectra_pf, h->spec_pf, e1 * (size_t)h->cfg.n_xspec);
+    if (h->cfg.bin_thermal) {
+        CPY(t->therm_d2N_sf, h->th_sf, psd_len(h)); CPY(t->therm_d2N_pf, h->th_pf, psd_len(h));
+        if (t->dNdp_cr_sf) { /* particle_counter.jl:81-85 */
+            for (int i = 0; i < h->n_grid; i++)
+                for (int k = 0; k < h->M + 2; k++) {
+                    double sum = 0.0;
+                    for (int j = 0; j < h->T + 2; j++) {
+                        double v = h->psd[(size_t)k + (size_t)(h->M + 2) * ((size_t)j + (size_t)(h->T + 2) * (size_t)i)];
+                        if (v > 0) sum += v;
+                    }
+                    t->dNdp_cr_sf[(size_t)k + (size_t)(h->M + 2) * (size_t)i] = sum;
+                }
+        }
+    }
     t->esc_flux = h->esc_flux; t->px_esc_feb = h->px_esc_feb; t->energy_esc_feb = h->en_esc_feb;
     t->sum_P_downstream = h->sumP; t->sum_KE_downstream = h->sumKE;
     t->px_esc_upstream = h->px_esc_up; t->energy_esc_upstream = h->en_esc_up;
