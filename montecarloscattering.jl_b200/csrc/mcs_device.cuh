@@ -478,6 +478,25 @@ __device__ __forceinline__ bool retro_time(const DevParams& P, Rng& rng, double&
     return lose;
 }
 
+// what get_dNdp_2D (particle_counter.jl:426-445) and thermo_calcs (thermo_calcs.jl:133-164) build from the
+// crossing log, accumulated on the fly so the log can stay small.  Out of line: only runs with cfg.bin_thermal.
+__device__ __noinline__ void bin_thermal_crossing(const DevParams& P, int lo, int hi, double sx, double ptot_sk, double gam_sk,
+                                                  double ux, double weight) {
+    const double w = weight * (ptot_sk > fabs(sx * SPIKE_AWAY) ? fabs(SPIKE_AWAY / ux) : fabs(gam_sk * P.aa * P.mp / sx));
+    const size_t sT = (size_t)(P.T + 2), sM = (size_t)(P.M + 2);
+    const int k = psd_bin_momentum(P, ptot_sk), jt = psd_bin_angle(P, sx, ptot_sk);
+    const double E0 = P.m * (P.c * P.c), etot = hypot(ptot_sk * P.c, E0);
+    for (int i = lo; i <= hi; i++) {
+        red_add_f64(&P.t.therm_sf[(size_t)jt + sT * ((size_t)k + sM * (size_t)(i - 1))], w);
+        const double g = P.gsf[i], b = P.ux[i] / P.c;
+        double pxX = g * (sx - b * etot / P.c);
+        const double ptX = sqrt((ptot_sk * ptot_sk - sx * sx) + pxX * pxX);
+        if (fabs(pxX) > ptX) pxX = copysign(ptX, pxX);
+        const int kX = psd_bin_momentum(P, ptX), jX = psd_bin_angle(P, pxX, ptX);
+        red_add_f64(&P.t.therm_pf[(size_t)jX + sT * ((size_t)kX + sM * (size_t)(i - 1))], w);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Process up to 32 queued events, one per lane, fully converged:
 //   crossing event -> all_flux.jl:86-158 (transform to the shock frame, flux / PSD / thermal-log tallies, x_spec spectra,
@@ -576,23 +595,7 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
                 if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
             }
         }
-        if (P.t.therm_sf != nullptr && nrec > 0) {
-            // what get_dNdp_2D (particle_counter.jl:426-445) and thermo_calcs (thermo_calcs.jl:133-164) build
-            // from the crossing log, accumulated on the fly so the log can stay small
-            const double w = weight * (ptot_sk > fabs(sx * SPIKE_AWAY) ? fabs(SPIKE_AWAY / ux) : fabs(gam_sk * P.aa * P.mp / sx));
-            const size_t sT = (size_t)(P.T + 2), sM = (size_t)(P.M + 2);
-            const int k = psd_bin_momentum(P, ptot_sk), jt = psd_bin_angle(P, sx, ptot_sk);
-            const double E0 = P.m * (P.c * P.c), etot = hypot(ptot_sk * P.c, E0);
-            for (int i = lo; i <= hi; i++) {
-                red_add_f64(&P.t.therm_sf[(size_t)jt + sT * ((size_t)k + sM * (size_t)(i - 1))], w);
-                const double g = P.gsf[i], b = P.ux[i] / P.c;
-                double pxX = g * (sx - b * etot / P.c);
-                const double ptX = sqrt((ptot_sk * ptot_sk - sx * sx) + pxX * pxX);
-                if (fabs(pxX) > ptX) pxX = copysign(ptX, pxX);
-                const int kX = psd_bin_momentum(P, ptX), jX = psd_bin_angle(P, pxX, ptX);
-                red_add_f64(&P.t.therm_pf[(size_t)jX + sT * ((size_t)kX + sM * (size_t)(i - 1))], w);
-            }
-        }
+        if (P.t.therm_sf != nullptr && nrec > 0) bin_thermal_crossing(P, lo, hi, sx, ptot_sk, gam_sk, ux, weight);
     }
     if (is_fin) {
         const int reason = (fl >> EV_REASON_SHIFT) & 7;
@@ -777,7 +780,12 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1, xsel = 0;
     bool down = false, inj = false, x_old_le0 = true;
     bool parked = true;  // the lane's next pass must take the general path (see the fast loop below)
+#ifdef MCS_SCHED_COUNTERS
     unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_slow_sec = 0, c_slow_lane = 0;  // scheduling statistics
+#define MCS_SC(x) x
+#else
+#define MCS_SC(x)
+#endif
     int qn = 0;  // events queued by this warp (warp-uniform)
     Rng rng;  // only ever passed to force-inlined helpers from here: stays in registers
     rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
@@ -842,9 +850,9 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         uint32_t ev = 0;       // crossing event to queue at point A
         bool moved = false;
         double x_old = 0.0;    // position before this pass's move
-        c_slow_sec++;
+        MCS_SC(c_slow_sec++;)
         if (ip >= 0 && parked) {
-            c_slow_lane++;
+            MCS_SC(c_slow_lane++;)
             helix++;
             if (MCS_UNLIKELY(helix > P.helix_cap)) {
                 fin = 1;  // K-1
@@ -1235,7 +1243,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                             if (ig != i_grid || (feb_x && ig <= P.i_grid_feb))
                                 fev = EV_VALID | (inj ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
                             prp_x = prp_n;
-                            helix++; c_fast_lane++;
+                            helix++; MCS_SC(c_fast_lane++;)
                             acct = acct_n; gper = gper_n; t_step = t_n; xsel = xsel_n;
                             pb = pb_n; pperp = pperp_n; phi = phi_n;
                             x_old_le0 = x <= 0.0; x = x_n; i_grid_old = i_grid; i_grid = ig; i_return = 2;
@@ -1261,7 +1269,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         }
                     }
                 }
-                c_fast_iter++;
+                MCS_SC(c_fast_iter++;)
                 const unsigned active = __ballot_sync(FULL, ip >= 0);
                 const unsigned waiting = __ballot_sync(FULL, (ip >= 0 && parked) || (ip < 0 && !queue_empty));
                 const int n_act = __popc(active), n_wait = __popc(waiting);
@@ -1275,8 +1283,8 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
     __syncwarp();
     if (qn > 0) process_events(P, wm, 0, qn);
 
-    count(P, CNT_FAST_LANE, c_fast_lane); count(P, CNT_SLOW_LANE, c_slow_lane);
-    if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_slow_sec); }
+    MCS_SC(count(P, CNT_FAST_LANE, c_fast_lane); count(P, CNT_SLOW_LANE, c_slow_lane);
+           if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_slow_sec); })
     // ---- block partials -------------------------------------------------------------------------------
     __syncthreads();
     const int np = 4 * ng + SC_N;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # time each build variant of the transport kernel on the bench workload (run under gpurun)
 N=${1:-1000000}
-for v in "" _128x5 _128x6 _256x3 _192x3; do
+for v in "" _16x64 _16x128 _8x128 _8x64; do
   lib=$PWD/montecarloscattering.jl_b200/libmcs_b200$v.so
   [ -f "$lib" ] || continue
   MCS_LIB=$lib timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --n-per-pcut $N 2>&1 | tail -1 | \
