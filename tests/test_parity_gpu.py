@@ -321,3 +321,68 @@ def test_deterministic_tallies_run_to_run(clib):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
     assert a.scalars == b.scalars and a.stats == b.stats
     assert rel_close(a.psd, b.psd, 0) < 1e-12
+
+
+def test_dynamic_queue_schedule_gives_same_particles(clib):
+    """cfg.dynamic_queue = 1 (global atomic work queue) changes only which lane runs which particle: per-particle outcomes are
+    identical, tallies agree to summation order."""
+    run = problem.setup_run(problem.planar_test_particle_input(20_000, momentum_cutoffs=LADDER[:3]))
+    out = []
+    for dyn in (0, 1):
+        cfg = driver.make_config(clib, run, na_cr=1000)
+        cfg.dynamic_queue = dyn
+        e = abi.Engine(clib, cfg)
+        start_ion(e, run)
+        n = e.population_size()
+        ns, steps = e.run_pcut(1, run.pcuts[0], 0.0)
+        e.split(run.inp.n_pts_pcut)
+        m = e.population_size()
+        ns2, steps2 = e.run_pcut(2, run.pcuts[1], run.pcuts[0])
+        out.append((ns, steps, ns2, steps2, e.get_fates(m), e.get_population(1, m), e.end_ion(want_log=False)))
+    a, b = out
+    assert a[:4] == b[:4]
+    for key in ("fate", "helix_count", "retro_steps", "n_draws"):
+        assert np.array_equal(a[4][key], b[4][key])
+    for key in ("ptot_pf", "pb_pf", "x_cm", "phi_rad", "grid", "l_save"):
+        assert np.array_equal(a[5][key], b[5][key]), key       # same code path per particle: bitwise equal
+    assert rel_close(a[6].pxx_flux, b[6].pxx_flux, 0) < 1e-12 and rel_close(a[6].psd, b[6].psd, 0) < 1e-11
+
+
+def test_spectra_and_fluxes_statistical_parity(olib, clib):
+    """north_star 'full runs': PSD spectra, flux profiles and escape sums of the kernel against the oracle with INDEPENDENT
+    random streams and injection draws.  The kernel is run R times (different seeds) to estimate the per-bin mean and
+    variance; the oracle's single run must be a draw from that distribution: sum of z^2 over the bins populated in every run
+    against chi-square at p > 1e-3 (neighbouring flux zones are positively correlated, which only makes this stricter), plus a
+    KS test of the spectrum's z scores against Student-t."""
+    from scipy import stats
+    inp = problem.planar_test_particle_input(4000, momentum_cutoffs=LADDER[:4])
+    run = problem.setup_run(inp)
+    R = 16
+
+    def one(lib, seed, threads=1):
+        e = make_engine(lib, run, seed=seed, threads=threads, na_cr=1000)
+        pop = problem.init_pop(run, run.profile, 1, np.random.default_rng(seed)).pop
+        start_ion(e, run, pop=pop)
+        e.run_ion(run.pcuts, problem.pcut_hi(inp.en_pcut_hi, run.species[0].mass), inp.n_pts_pcut, inp.n_pts_pcut_hi)
+        t = e.end_ion(want_log=False)
+        spec = t.psd.sum(axis=(0, 1))                    # dN(p) summed over zones and angles
+        return dict(spec=spec, pxx=t.pxx_flux.copy(), en=t.energy_flux.copy(), sumP=np.array([t.scalars["sum_P_downstream"]]),
+                    esc_dn=t.esc_psd_feb_downstream.sum(axis=0))
+
+    g = [one(clib, 1000 + r) for r in range(R)]
+    o = one(olib, 77, threads=8)
+    z_all = []
+    for key in ("spec", "pxx", "en", "sumP", "esc_dn"):
+        G = np.array([x[key] for x in g])
+        mean, sd = G.mean(axis=0), G.std(axis=0, ddof=1)
+        ok = (sd > 0) & (np.count_nonzero(G, axis=0) == R) & (np.abs(mean) > 20 * sd / np.sqrt(R) * 0 + 0)  # populated in every run
+        z = (o[key][ok] - mean[ok]) / (sd[ok] * np.sqrt(1 + 1 / R))
+        assert z.size > 0, key
+        chi2 = float((z**2).sum())
+        # z^2 of a Student-t with R-1 dof has mean (R-1)/(R-3): scale to a chi-square reference
+        p = stats.chi2.sf(chi2 * (R - 3) / (R - 1), z.size)
+        print(f"\n[{key}] bins {z.size}  chi2/ndf {chi2 / z.size:.2f}  p {p:.3g}  max|z| {np.abs(z).max():.2f}")
+        assert p > 1e-3, (key, chi2, z.size)
+        z_all.append(z)
+    # the momentum spectrum's bins are nearly independent: its z scores must also look like draws from Student-t(R-1)
+    assert stats.kstest(z_all[0], stats.t(df=R - 1).cdf).pvalue > 1e-3
