@@ -278,6 +278,9 @@ MCS_API int mcs_measure_atomic_peak(McsHandle* h, int64_t n_cells, double* gops)
 /* Rate [steps/s] of the bare arithmetic of one bulk scattering step (Philox + kick + phase + move)
  * with no control flow around it: the practical ceiling of the transport kernel's hot path on this device. */
 MCS_API int mcs_measure_scatter_peak(McsHandle* h, double* steps_per_s);
+/* Device self-test of the branch-free sqrt / division sequences of the fast loop (csrc/mcs_math.cuh): n operand pairs
+ * drawn over the kernel's ranges, each compared bit for bit with the IEEE sqrt() and `/`; returns the mismatch counts. */
+MCS_API int mcs_selftest_math(McsHandle* h, int64_t n, int64_t* n_bad_sqrt, int64_t* n_bad_div);
 
 #ifdef __cplusplus
 }

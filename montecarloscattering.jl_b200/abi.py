@@ -112,7 +112,7 @@ ABI_SYMBOLS = (
     "mcs_comm_unique_id", "mcs_comm_init", "mcs_set_profile", "mcs_begin_ion", "mcs_run_pcut", "mcs_split", "mcs_split_explicit",
     "mcs_run_ion", "mcs_end_ion", "mcs_get_population", "mcs_population_size", "mcs_get_fates",
     "mcs_replay_set_stream", "mcs_trace_enable", "mcs_trace_get", "mcs_get_timing", "mcs_measure_fp64_peak",
-    "mcs_measure_atomic_peak", "mcs_measure_scatter_peak",
+    "mcs_measure_atomic_peak", "mcs_measure_scatter_peak", "mcs_selftest_math",
 )
 
 
@@ -156,6 +156,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mcs_measure_fp64_peak.argtypes = [H, _pd]
     lib.mcs_measure_atomic_peak.argtypes = [H, _i64, _pd]
     lib.mcs_measure_scatter_peak.argtypes = [H, _pd]
+    lib.mcs_selftest_math.argtypes = [H, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     sizes = (_i32 * 6)()
     lib.mcs_abi_sizes(C.byref(sizes))
     want = [C.sizeof(t) for t in (McsConfig, McsSpecies, McsTallies, McsPopulation, McsTraceRec, McsTiming)]
@@ -390,6 +391,11 @@ class Engine:
         v = _d()
         self._check(self.lib.mcs_measure_scatter_peak(self._h, C.byref(v)))
         return v.value
+
+    def selftest_math(self, n: int) -> tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.mcs_selftest_math(self._h, n, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def measure_atomic_peak(self, n_cells: int) -> float:
         v = _d()

@@ -859,3 +859,19 @@ extern "C" int mcs_measure_scatter_peak(McsHandle* h, double* steps_per_s) {
     *steps_per_s = best;
     return MCS_OK;
 }
+
+extern "C" int mcs_selftest_math(McsHandle* h, int64_t n, int64_t* n_bad_sqrt, int64_t* n_bad_div) {
+    if (!h || !n_bad_sqrt || !n_bad_div || n <= 0) return fail(MCS_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    unsigned long long out[2] = {0, 0};
+    CU(cudaMalloc(&d, 16));
+    CU(cudaMemsetAsync(d, 0, 16, h->stream));
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((long long)n, h->P.key0, h->P.key1, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    *n_bad_sqrt = (int64_t)out[0]; *n_bad_div = (int64_t)out[1];
+    return MCS_OK;
+}

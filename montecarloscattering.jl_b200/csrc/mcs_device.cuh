@@ -1175,15 +1175,16 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         const double phi_s = u2 * TWO_PI - PI;
                         double sps, cps;
                         sincos_bf(phi_s, &sps, &cps);
-                        const double sin_d = sqrt(sd2);
+                        // sqrt_nr/div_nr: NaN for sd2 == 0 or sn2 <= 0 -> sn2 / x_n turn NaN -> the lane parks below
+                        const double sin_d = sqrt_nr(sd2);
                         const double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
                         const double sn2 = 1 - cos_new * cos_new;
-                        const double sin_new = sqrt(sn2);
+                        const double sin_new = sqrt_nr(sn2);
                         double phi_p = phi + HALF_PI;
                         {
-                            double sv = sps * sin_d / sin_new;
+                            double sv = div_nr(sps * sin_d, sin_new);
                             if (fabs(sv) > SIN_UPPER_LIMIT) sv = copysign(SIN_UPPER_LIMIT, sv);
-                            phi_p += asin_bf(sv);
+                            phi_p += asin_bf<true>(sv);
                         }
                         const double phi_sc = phi_p - HALF_PI;
                         const double pb_n = ptot * cos_new, pperp_n = ptot * sin_new;
@@ -1456,6 +1457,25 @@ __global__ void fill_defaults_kernel(PopPtrs p, long long n, int has_down, int h
     if (!has_tcut) p.tcut[i] = 1;
 }
 
+// sqrt_nr / div_nr against the IEEE operations on operands spread over the fast loop's ranges (mcs_math.cuh).
+__global__ void selftest_math_kernel(long long n, uint32_t key0, uint32_t key1, unsigned long long* bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0xABCDu, 7u, key0, key1, o0, o1, o2, o3);
+    const double u = u53(o1, o0), v = u53(o3, o2);
+    // operands: 1 - c^2 for c near +-1 (sin^2 of small and large angles), plain (0,1], and a wide log-uniform sweep
+    double xs, a, b;
+    switch (i & 3) {
+        case 0: { const double c = 1 - u * exp2(-40.0 * v); xs = 1 - c * c; a = 2 * v - 1; b = sqrt(fmax(xs, 1e-300)); break; }
+        case 1: xs = u; a = 2 * v - 1; b = 0.25 + 0.75 * u; break;
+        case 2: xs = exp2(1900.0 * u - 950.0); a = (2 * v - 1) * exp2(200.0 * u - 100.0); b = exp2(200.0 * v - 100.0); break;
+        default: xs = (1 - u) * 0.5; a = u * u * v; b = 1 - 0.7 * u; break;
+    }
+    if (xs >= 0x1.0p-960 && __double_as_longlong(sqrt_nr(xs)) != __double_as_longlong(sqrt(xs))) atomicAdd(&bad[0], 1ull);
+    if (b != 0.0 && __double_as_longlong(div_nr(a, b)) != __double_as_longlong(a / b)) atomicAdd(&bad[1], 1ull);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Roofline denominators measured in place (MEASURED_PEAKS.json has no FP64 entry).
 __global__ void dfma_peak_kernel(double* out, int iters) {
@@ -1483,17 +1503,17 @@ __global__ void __launch_bounds__(256, 2) scatter_only_kernel(double* out, int i
         const double u1 = u53(o1, o0), u2 = u53(o3, o2);
         const double cos_old = pb * inv_ptot, sin_old = pperp * inv_ptot;
         const double cos_d = 1 - u1 * omc;
-        const double sin_d = sqrt(fmax(1 - cos_d * cos_d, 0.0));
+        const double sin_d = sqrt_nr(fmax(1 - cos_d * cos_d, 0x1.0p-900));
         const double phi_s = u2 * TWO_PI - PI;
         double sps, cps;
         sincos_bf(phi_s, &sps, &cps);
         const double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
-        const double sin_new = sqrt(fmax(1 - cos_new * cos_new, 0.0));
+        const double sin_new = sqrt_nr(fmax(1 - cos_new * cos_new, 0x1.0p-900));
         pb = ptot * cos_new;
         pperp = ptot * sin_new;
-        double s = sps * sin_d / sin_new;
+        double s = div_nr(sps * sin_d, sin_new);
         if (fabs(s) > SIN_UPPER_LIMIT) s = copysign(SIN_UPPER_LIMIT, s);
-        phi = (phi + HALF_PI + asin_bf(s)) - HALF_PI;
+        phi = (phi + HALF_PI + asin_bf<true>(s)) - HALF_PI;
         const double t_step = gper * inv_xn;
         phi = mod2pi(phi + dphi);
         x = x + gsf * (pb * t_step * inv_gm + ux * t_step);

@@ -1117,6 +1117,7 @@ int mcs_get_timing(McsHandle* h, McsTiming* out, int32_t reset) {
 }
 int mcs_measure_fp64_peak(McsHandle* h, double* t) { (void)h; (void)t; return fail(MCS_ERR_UNSUPPORTED, "cpu oracle"); }
 int mcs_measure_scatter_peak(McsHandle* h, double* r) { (void)h; (void)r; return fail(MCS_ERR_UNSUPPORTED, "cpu oracle"); }
+int mcs_selftest_math(McsHandle* h, int64_t n, int64_t* a, int64_t* b) { (void)h; (void)n; (void)a; (void)b; return fail(MCS_ERR_UNSUPPORTED, "cpu oracle"); }
 int mcs_measure_atomic_peak(McsHandle* h, int64_t n, double* g) {
     (void)h; (void)n; (void)g;
     return fail(MCS_ERR_UNSUPPORTED, "cpu oracle");

@@ -311,6 +311,14 @@ def test_fast_loop_matches_general_path(clib, monkeypatch):
     assert rel_close(ta.pxx_flux, tb.pxx_flux, 0) < 1e-11 and rel_close(ta.psd, tb.psd, 0) < 1e-9
 
 
+def test_branch_free_sqrt_and_division_are_ieee(clib):
+    """The fast loop's sqrt_nr / div_nr (csrc/mcs_math.cuh: the seed + Newton sequence of sqrt.rn.f64 / div.rn.f64 without
+    the special-operand branch) against sqrt() and `/` on 1e8 operands over the kernel's ranges: bit for bit."""
+    run = problem.setup_run(problem.planar_test_particle_input(1000, momentum_cutoffs=LADDER[:2]))
+    e = make_engine(clib, run)
+    assert e.selftest_math(100_000_000) == (0, 0)
+
+
 def test_deterministic_tallies_run_to_run(clib):
     """Default (static) schedule: the per-warp / per-block partials are reduced in a fixed order, so the flux tallies and
     scalars are bitwise identical run to run (the PSD takes L2 atomics and is only required to agree to rounding)."""
