@@ -134,6 +134,8 @@ def main():
     ap.add_argument("--n-per-pcut", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=10000, help="particles per pcut of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generate-in-library", action="store_true",
+                    help="SURVEY 8(f2): hand init_pop to the library in run-length form instead of copying host arrays")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -203,23 +205,30 @@ def main():
         eng.comm_init(rank, world, bytes(uid.cpu().tolist()))
 
     # host inputs of one step, in pinned memory (the population main_loops.jl hands to the particle loop)
-    ip = problem.init_pop(run, prof, 1, np.random.default_rng(0), shuffle=True)
-    lo, hi = driver.shard_bounds(len(ip.pop["weight"]), rank, world)
+    spec = problem.injection_spec(run, prof, 1)
+    lo, hi = driver.shard_bounds(spec.n, rank, world)
     pinned, pop = [], {}
-    for k, v in ip.pop.items():
-        t = torch.from_numpy(np.ascontiguousarray(v[lo:hi])).pin_memory()
-        pinned.append(t)
-        pop[k] = t.numpy()
+    if not a.generate_in_library:
+        ip = problem.expand_injection(spec, np.random.default_rng(0), shuffle=True)
+        for k, v in ip.pop.items():
+            t = torch.from_numpy(np.ascontiguousarray(v[lo:hi])).pin_memory()
+            pinned.append(t)
+            pop[k] = t.numpy()
     eps = problem.populate_eps_target(run, prof)
     sp = driver.species_struct(run, 1)
     p_hi = problem.pcut_hi(run.inp.en_pcut_hi, run.species[0].mass)
     h2d = sum(v.nbytes for v in pop.values()) + 11 * (run.n_grid + 2) * 8
+    if a.generate_in_library:
+        h2d += 6 * 8 * len(spec.bin_ptot) + 8
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def one_step():
         """The call sequence a Julia user makes per (iteration, ion): H2D, the device pcut loop, D2H."""
         eng.set_profile(prof, eps, np.zeros(run.n_grid))
-        eng.begin_ion(1, 1, sp, pop, first_global=lo)
+        if a.generate_in_library:
+            eng.begin_ion_generate(1, 1, sp, spec, first_global=lo, n_local=hi - lo, shuffle=True)
+        else:
+            eng.begin_ion(1, 1, sp, pop, first_global=lo)
         n_run, n_used, n_saved = eng.run_ion(run.pcuts, p_hi, run.inp.n_pts_pcut, run.inp.n_pts_pcut_hi)
         t = eng.end_ion(want_psd=True, want_log=False)
         return t, n_run
@@ -274,6 +283,8 @@ def main():
             "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(a.workload, run, a.n_per_pcut, {
+                "population": "generated in the library from the run-length injection list" if a.generate_in_library
+                              else "host arrays in pinned memory, copied every step",
                 "pcuts_run": int(n_run), "steps_per_iteration": int(steps_per_iter), "l2": "flushed between timed iterations",
                 "s_per_iteration_device": dev_s / a.steps, "s_per_iteration_e2e": wall_s / a.steps}),
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

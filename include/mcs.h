@@ -232,6 +232,42 @@ MCS_API int mcs_set_profile(McsHandle* h, int32_t n_grid, const double* x_grid_c
 MCS_API int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies* sp, int64_t n_pts,
                           int64_t first_global, const McsPopulation* pop);
 
+/* init_pop (initializers.jl:977-1134) in run-length form, so that the injected population is generated
+ * where it is used instead of being drawn on the host and copied (0.5 GB per ion at 1e7 particles).  Particle j of the
+ * momentum-ordered population (j = 0 .. n-1, n = sum of bin_count) belongs to the bin b with bin_start[b] <= j <
+ * bin_start[b+1] and gets  ptot = bin_ptot[b], weight = bin_weight[b], x = x_cm, grid = grid, two uniforms (U1, U2) from
+ * the Philox block with counter (0, j, i_ion << 16, i_iter) — pcut field 0, never used by the transport — and
+ *   mode MCS_INJ_UPSTREAM        pb = (ptot * 2) * (U1 - 0.5)                                   initializers.jl:1006
+ *   mode MCS_INJ_FASTPUSH_NONREL vx = lo + (hi - lo) * sqrt(U1);  pb = gfac * (vx - u_stop)     initializers.jl:1119-1131
+ *   mode MCS_INJ_FASTPUSH_REL    bx = lo + (hi - lo) * sqrt(U1);  pb = gfac * ((bx - bu) / (1 - bx * bu) * c),  bu = u_stop / c
+ *                                                                                               initializers.jl:1095-1117
+ *   phi = (2 pi) * U2                                                                           ion_init.jl:51
+ * with lo, hi, gfac the per-bin bin_lo / bin_hi / bin_gfac (computed by the caller, so that only IEEE sqrt / add / mul /
+ * div remain per particle).  Slot s of the population holds particle j = perm(s): perm_stride = 0 is the identity;
+ * perm_stride = K lays the K strided sub-sequences (0, K, 2K, ...), (1, K+1, ...), ... end to end, which makes every
+ * contiguous shard a fair sample of the distribution.  The remaining fields take the reference's initial
+ * values (ion_init.jl:29-53). */
+enum { MCS_INJ_UPSTREAM = 0, MCS_INJ_FASTPUSH_NONREL = 1, MCS_INJ_FASTPUSH_REL = 2 };
+typedef struct McsInjection {
+    int32_t n_bins;
+    int32_t mode;
+    const double* bin_ptot;   /* [n_bins] */
+    const double* bin_weight; /* [n_bins] */
+    const int64_t* bin_start; /* [n_bins + 1] exclusive prefix sum of the per-bin particle counts */
+    const double* bin_lo;     /* [n_bins] (fast push) */
+    const double* bin_hi;     /* [n_bins] (fast push) */
+    const double* bin_gfac;   /* [n_bins] (fast push) */
+    double x_cm;
+    double u_stop;
+    int64_t grid;
+    int32_t perm_stride;
+    int32_t reserved;
+} McsInjection;
+/* mcs_begin_ion with the population generated in place: this rank holds slots first_global .. first_global + n_local - 1
+ * of the n_total = bin_start[n_bins] particles. */
+MCS_API int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies* sp, int64_t first_global,
+                                   int64_t n_local, const McsInjection* inj);
+
 /* == main_loops.jl:184-292 for one pcut, on device. n_saved / n_steps are this rank's. */
 MCS_API int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_prev, int64_t* n_saved,
                          int64_t* n_steps);

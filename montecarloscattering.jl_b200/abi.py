@@ -83,6 +83,14 @@ class McsPopulation(C.Structure):
     ]
 
 
+class McsInjection(C.Structure):
+    _fields_ = [
+        ("n_bins", _i32), ("mode", _i32), ("bin_ptot", _pd), ("bin_weight", _pd), ("bin_start", _pi64),
+        ("bin_lo", _pd), ("bin_hi", _pd), ("bin_gfac", _pd), ("x_cm", _d), ("u_stop", _d), ("grid", _i64),
+        ("perm_stride", _i32), ("reserved", _i32),
+    ]
+
+
 class McsTraceRec(C.Structure):
     _fields_ = [
         ("x_cm", _d), ("ptot_pf", _d), ("pb_pf", _d), ("phi_rad", _d), ("acctime_sec", _d), ("prp_x_cm", _d),
@@ -109,7 +117,7 @@ POP_U8 = ("downstream", "inj")
 # every symbol include/mcs.h declares
 ABI_SYMBOLS = (
     "mcs_last_error", "mcs_backend", "mcs_abi_sizes", "mcs_default_config", "mcs_create", "mcs_destroy",
-    "mcs_comm_unique_id", "mcs_comm_init", "mcs_set_profile", "mcs_begin_ion", "mcs_run_pcut", "mcs_split", "mcs_split_explicit",
+    "mcs_comm_unique_id", "mcs_comm_init", "mcs_set_profile", "mcs_begin_ion", "mcs_begin_ion_generate", "mcs_run_pcut", "mcs_split", "mcs_split_explicit",
     "mcs_run_ion", "mcs_end_ion", "mcs_get_population", "mcs_population_size", "mcs_get_fates",
     "mcs_replay_set_stream", "mcs_trace_enable", "mcs_trace_get", "mcs_get_timing", "mcs_measure_fp64_peak",
     "mcs_measure_atomic_peak", "mcs_measure_scatter_peak", "mcs_selftest_math",
@@ -140,6 +148,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mcs_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.mcs_set_profile.argtypes = [H, _i32] + [_pd] * 11
     lib.mcs_begin_ion.argtypes = [H, _i32, _i32, C.POINTER(McsSpecies), _i64, _i64, C.POINTER(McsPopulation)]
+    lib.mcs_begin_ion_generate.argtypes = [H, _i32, _i32, C.POINTER(McsSpecies), _i64, _i64, C.POINTER(McsInjection)]
     lib.mcs_run_pcut.argtypes = [H, _i32, _d, _d, _pi64, _pi64]
     lib.mcs_split.argtypes = [H, _i64, _pi64, _pi64, _pi64]
     lib.mcs_split_explicit.argtypes = [H, _i64, _i64, _pi64]
@@ -275,6 +284,22 @@ class Engine:
         n = len(pop["weight"])
         st, keep = self._pop_struct(pop, n)
         self._check(self.lib.mcs_begin_ion(self._h, i_iter, i_ion, C.byref(species), n, first_global, C.byref(st)))
+
+    def begin_ion_generate(self, i_iter: int, i_ion: int, species: McsSpecies, spec, first_global: int = 0,
+                           n_local: int | None = None, shuffle: bool = False):
+        """mcs_begin_ion_generate from a problem.InjectionSpec: the population is produced inside the library."""
+        keep = [np.ascontiguousarray(a, np.float64) for a in (spec.bin_ptot, spec.bin_weight, spec.bin_lo, spec.bin_hi,
+                                                              spec.bin_gfac)]
+        start = np.concatenate(([0], np.cumsum(spec.bin_count))).astype(np.int64)
+        n_total = int(start[-1])
+        inj = McsInjection(n_bins=len(keep[0]), mode=spec.mode, bin_ptot=_ptr(keep[0], _pd), bin_weight=_ptr(keep[1], _pd),
+                           bin_start=_ptr(start, _pi64), bin_lo=_ptr(keep[2], _pd), bin_hi=_ptr(keep[3], _pd),
+                           bin_gfac=_ptr(keep[4], _pd), x_cm=spec.x_cm, u_stop=spec.u_stop, grid=spec.grid,
+                           perm_stride=64 if shuffle else 0, reserved=0)
+        n_local = n_total - first_global if n_local is None else n_local
+        self._check(self.lib.mcs_begin_ion_generate(self._h, i_iter, i_ion, C.byref(species), first_global, n_local,
+                                                    C.byref(inj)))
+        return n_total
 
     def run_pcut(self, i_pcut: int, pcut: float, pcut_prev: float):
         ns, nst = _i64(), _i64()

@@ -123,6 +123,7 @@ struct McsHandle {
     int max_blocks = 0, block = 256, blocks_per_sm = 2;
     // debug
     double* d_replay_u = nullptr;
+    double* d_inj = nullptr;  // packed injection bins (mcs_begin_ion_generate)
     long long* d_replay_off = nullptr;
     long long replay_n = 0;
     int* d_trace_slot = nullptr;
@@ -166,7 +167,7 @@ extern "C" int mcs_destroy(McsHandle* h) {
     cudaFree(h->d_l_save); cudaFree(h->d_fate); cudaFree(h->d_helix); cudaFree(h->d_retro); cudaFree(h->d_draws);
     cudaFree(h->d_saved_idx); cudaFree(h->d_block_off); cudaFree(h->d_total); cudaFree(h->d_block_cnt);
     cudaFree(h->d_tally); cudaFree(h->d_u64); cudaFree(h->d_tg); cudaFree(h->d_tpx); cudaFree(h->d_tpt); cudaFree(h->d_tw);
-    cudaFree(h->d_partials); cudaFree(h->d_replay_u); cudaFree(h->d_replay_off); cudaFree(h->d_trace_slot);
+    cudaFree(h->d_inj); cudaFree(h->d_partials); cudaFree(h->d_replay_u); cudaFree(h->d_replay_off); cudaFree(h->d_trace_slot);
     cudaFree(h->d_trace_recs); cudaFree(h->d_trace_cnt); cudaFree(h->d_gather); cudaFree(h->d_xchg);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -386,6 +387,56 @@ extern "C" int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const 
         fill_defaults_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
             p, n, pop->downstream != nullptr, pop->inj != nullptr, pop->xn_per != nullptr, pop->prp_x_cm != nullptr,
             pop->acctime_sec != nullptr, pop->tcut != nullptr, h->cfg.xn_per_fine, h->cfg.x_grid_stop);
+        h->tm.other_launches++;
+    }
+    CU(cudaEventRecord(h->ev3, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+    h->tm.h2d_ms += ms;
+    h->have_ion = true;
+    return MCS_OK;
+}
+
+extern "C" int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies* sp, int64_t first_global,
+                                      int64_t n_local, const McsInjection* inj) {
+    if (!h || !sp || !inj) return fail(MCS_ERR_ARG, "null argument");
+    if (!h->have_profile) return fail(MCS_ERR_STATE, "mcs_set_profile first");
+    if (i_ion < 1 || i_ion > h->cfg.n_ions) return fail(MCS_ERR_ARG, "i_ion out of range");
+    if (inj->n_bins < 1 || !inj->bin_ptot || !inj->bin_weight || !inj->bin_start) return fail(MCS_ERR_ARG, "injection bins missing");
+    if (inj->mode < 0 || inj->mode > 2) return fail(MCS_ERR_ARG, "injection mode");
+    if (inj->mode != MCS_INJ_UPSTREAM && (!inj->bin_lo || !inj->bin_hi || !inj->bin_gfac)) return fail(MCS_ERR_ARG, "fast-push bins missing");
+    const int nb = inj->n_bins;
+    const int64_t n_total = inj->bin_start[nb];
+    if (n_local < 0 || first_global < 0 || first_global + n_local > n_total) return fail(MCS_ERR_ARG, "shard outside the population");
+    if (n_local > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "n_pts exceeds n_pts_max");
+    if (inj->grid < 0 || inj->grid > h->ng + 1) return fail(MCS_ERR_ARG, "grid index out of range");
+    CU(cudaSetDevice(h->device));
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion;
+    h->n_use = n_local; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
+    CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
+    CU(cudaMemsetAsync(h->d_u64, 0, (size_t)(h->ng + CNT_N) * 8, h->stream));
+    memset(h->h_counters, 0, sizeof h->h_counters);
+    CU(cudaEventRecord(h->ev2, h->stream));
+    // bins: one packed upload [ptot | weight | lo | hi | gfac | start]
+    std::vector<double> pack((size_t)nb * 5 + (size_t)nb + 1, 0.0);
+    for (int b = 0; b < nb; b++) {
+        pack[b] = inj->bin_ptot[b]; pack[nb + b] = inj->bin_weight[b];
+        if (inj->mode != MCS_INJ_UPSTREAM) { pack[2 * nb + b] = inj->bin_lo[b]; pack[3 * nb + b] = inj->bin_hi[b]; pack[4 * nb + b] = inj->bin_gfac[b]; }
+    }
+    memcpy(&pack[(size_t)5 * nb], inj->bin_start, (size_t)(nb + 1) * 8);
+    cudaFree(h->d_inj); h->d_inj = nullptr;
+    CU(cudaMalloc(&h->d_inj, pack.size() * 8));
+    CU(cudaMemcpyAsync(h->d_inj, pack.data(), pack.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    InjDev J;
+    J.ptot = h->d_inj; J.weight = h->d_inj + nb; J.lo = h->d_inj + 2 * nb; J.hi = h->d_inj + 3 * nb; J.gfac = h->d_inj + 4 * nb;
+    J.start = reinterpret_cast<const long long*>(h->d_inj + 5 * nb);
+    J.n_bins = nb; J.mode = inj->mode; J.perm_stride = inj->perm_stride; J.n_total = n_total; J.grid = inj->grid;
+    J.x_cm = inj->x_cm; J.u_stop = inj->u_stop; J.c = h->cfg.c_cms; J.xn_fine = h->cfg.xn_per_fine; J.x_grid_stop = h->cfg.x_grid_stop;
+    J.key0 = h->P.key0; J.key1 = h->P.key1; J.ctr2 = (uint32_t)i_ion << 16; J.ctr3 = (uint32_t)i_iter;
+    if (n_local > 0) {
+        generate_population_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, h->stream>>>(h->pop[h->cur], n_local, first_global, J);
+        CU(cudaGetLastError());
         h->tm.other_launches++;
     }
     CU(cudaEventRecord(h->ev3, h->stream));

@@ -1457,6 +1457,48 @@ __global__ void fill_defaults_kernel(PopPtrs p, long long n, int has_down, int h
     if (!has_tcut) p.tcut[i] = 1;
 }
 
+// init_pop in run-length form (include/mcs.h McsInjection; initializers.jl:977-1134, ion_init.jl:29-53).  HBM-bound: 82 B
+// written per particle, bins (<= 151 x 6 doubles) read through L1.  Every operation is an explicitly rounded IEEE one
+// (no FMA contraction), so the population is bit-identical to the oracle's and the host mirror's.
+struct InjDev {
+    const double *ptot, *weight, *lo, *hi, *gfac;
+    const long long* start;
+    int n_bins, mode, perm_stride;
+    long long n_total, grid;
+    double x_cm, u_stop, c, xn_fine, x_grid_stop;
+    uint32_t key0, key1, ctr2, ctr3;
+};
+__global__ void generate_population_kernel(PopPtrs p, long long n_local, long long first_global, InjDev J) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    long long s = first_global + i, j = s;
+    if (J.perm_stride > 0) {
+        const long long K = J.perm_stride, a = J.n_total / K, b = J.n_total % K;
+        if (s < b * (a + 1)) j = s / (a + 1) + K * (s % (a + 1));
+        else { s -= b * (a + 1); j = (b + s / a) + K * (s % a); }
+    }
+    int lo = 0, hi = J.n_bins;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (J.start[mid] <= j) lo = mid; else hi = mid; }
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10(0u, (uint32_t)j, J.ctr2, J.ctr3, J.key0, J.key1, o0, o1, o2, o3);
+    const double u1 = u53(o1, o0), u2 = u53(o3, o2);
+    const double ptot = J.ptot[lo];
+    double pb;
+    if (J.mode == MCS_INJ_UPSTREAM) pb = __dmul_rn(__dmul_rn(ptot, 2.0), __dadd_rn(u1, -0.5));
+    else {
+        const double l = J.lo[lo];
+        const double vx = __dadd_rn(l, __dmul_rn(__dadd_rn(J.hi[lo], -l), __dsqrt_rn(u1)));
+        if (J.mode == MCS_INJ_FASTPUSH_REL) {
+            const double bu = __ddiv_rn(J.u_stop, J.c);
+            const double vpf = __dmul_rn(__ddiv_rn(__dadd_rn(vx, -bu), __dadd_rn(1.0, -__dmul_rn(vx, bu))), J.c);
+            pb = __dmul_rn(J.gfac[lo], vpf);
+        } else pb = __dmul_rn(J.gfac[lo], __dadd_rn(vx, -J.u_stop));
+    }
+    p.weight[i] = J.weight[lo]; p.ptot[i] = ptot; p.pb[i] = pb; p.x[i] = J.x_cm; p.grid[i] = J.grid;
+    p.phi[i] = __dmul_rn(TWO_PI, u2);
+    p.down[i] = 0; p.inj[i] = 0; p.xn_per[i] = J.xn_fine; p.prp_x[i] = J.x_grid_stop; p.acctime[i] = 0.0; p.tcut[i] = 1;
+}
+
 // sqrt_nr / div_nr against the IEEE operations on operands spread over the fast loop's ranges (mcs_math.cuh).
 __global__ void selftest_math_kernel(long long n, uint32_t key0, uint32_t key1, unsigned long long* bad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -145,13 +145,14 @@ def reduce_tallies_host(t: abi.Tallies, comm) -> abi.Tallies:
 
 def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = None, comm=None,
                device_comm: bool = False, want_psd: bool = True, want_log: bool = True, profile_update=None,
-               host_pcut_loop: bool = False, shuffle_population: bool = False):
+               host_pcut_loop: bool = False, shuffle_population: bool = False, generate_in_library: bool = False):
     """loop_itr / loop_ion / loop_pcut of main_loops.jl:52-341.
 
     Returns a list (per iteration) of lists (per ion) of dicts with the per-ion tallies (pure sums),
     the flux arrays as the reference holds them (fast-push prefill + sums + 1e-99 floor) and the pcut
     bookkeeping.  `comm` shards the population over ranks; `device_comm` means the engine already
-    reduces inside the library (NCCL) so the host must not reduce again.
+    reduces inside the library (NCCL) so the host must not reduce again.  `generate_in_library` hands init_pop to the
+    library in run-length form (mcs_begin_ion_generate): nothing per-particle is drawn or copied by the host.
     """
     inp = run.inp
     prof = run.profile
@@ -167,13 +168,20 @@ def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = No
             if sp.n0 == 0 and inp.skip_zero_density_species:  # SURVEY B-11
                 per_ion.append(None)
                 continue
-            rng = np.random.default_rng((i_iter - 1) * run.n_ions + (i_ion - 1))  # stands in for :120-121
-            ip = problem.init_pop(run, prof, i_ion, rng, shuffle=shuffle_population)
-            n = len(ip.pop["weight"])
-            lo, hi = shard_bounds(n, rank, world)
-            pop = {k: v[lo:hi] for k, v in ip.pop.items()}
             engine.set_profile(prof, eps_target, pool.copy())  # energy_recv_pool .= energy_transfer_pool  :164
-            engine.begin_ion(i_iter, i_ion, species_struct(run, i_ion), pop, first_global=lo)
+            if generate_in_library:
+                ip = problem.injection_spec(run, prof, i_ion)
+                n = ip.n
+                lo, hi = shard_bounds(n, rank, world)
+                engine.begin_ion_generate(i_iter, i_ion, species_struct(run, i_ion), ip, first_global=lo, n_local=hi - lo,
+                                          shuffle=shuffle_population)
+            else:
+                rng = np.random.default_rng((i_iter - 1) * run.n_ions + (i_ion - 1))  # stands in for :120-121
+                ip = problem.init_pop(run, prof, i_ion, rng, shuffle=shuffle_population)
+                n = len(ip.pop["weight"])
+                lo, hi = shard_bounds(n, rank, world)
+                pop = {k: v[lo:hi] for k, v in ip.pop.items()}
+                engine.begin_ion(i_iter, i_ion, species_struct(run, i_ion), pop, first_global=lo)
             p_hi = problem.pcut_hi(inp.en_pcut_hi, sp.mass)
             if host_pcut_loop or (comm is not None and not device_comm):
                 n_run, n_used, n_saved = run_ion_host_comm(engine, run.pcuts, p_hi, inp.n_pts_pcut,

@@ -550,9 +550,10 @@ def _mb_bin_area(p1, p2, E1, E2):
     return (p2 - p1) * (f1 + f2) / 2
 
 
-def set_inj_dist(inj_weight: bool, n_pts_inj: int, inp_distr: int, T_or_E: float, m: float, n0: float,
-                 compat_zero_first=False):
-    """initializers.jl:1251-1328 with its helpers :1330-1514. Returns (ptot[n], weight[n])."""
+def inj_bins(inj_weight: bool, n_pts_inj: int, inp_distr: int, T_or_E: float, m: float, n0: float,
+             compat_zero_first=False):
+    """initializers.jl:1251-1328 with its helpers :1330-1514 in run-length form: the injected particles are
+    `count[b]` copies of (ptot[b], weight[b]), bins in order of momentum.  Returns (ptot[nb], weight[nb], count[nb])."""
     if not 0 < inp_distr < 3:
         raise ValueError("Code can only do inp_distr = 1 or 2.")
     nb = NUM_THERM_BINS
@@ -577,119 +578,224 @@ def set_inj_dist(inj_weight: bool, n_pts_inj: int, inp_distr: int, T_or_E: float
     centres = np.array([math.sqrt(p_range[i] * p_range[i + 1]) for i in range(nb)])
     if inj_weight:
         area_per_pt = area_tot / n_pts_inj
-        counts = np.array([int(np.round(a / area_per_pt)) for a in areas])  # Julia round(Int, x): ties to even
-        ptot = np.repeat(centres, counts)
+        counts = np.array([int(np.round(a / area_per_pt)) for a in areas], np.int64)  # Julia round(Int, x): ties to even
+        ptot = centres
         if compat_zero_first:  # `n_pts_tot = 1` at :1425 leaves slot 1 at ptot = 0 (SURVEY B-7)
             ptot = np.concatenate(([0.0], ptot))
-        n = len(ptot)
-        weight = np.full(n, n0 / n)
+            counts = np.concatenate(([1], counts)).astype(np.int64)
+        n = int(counts.sum())
+        weight = np.full(len(ptot), n0 / n)
     else:
         n_per_bin = n_pts_inj // nb
         if n_per_bin < 5:
             raise ValueError("too few particles per bin; increase n_pts_inj")
-        ptot = np.repeat(centres, n_per_bin)
-        weight = np.repeat(np.array([a / area_tot / n_per_bin * n0 for a in areas]), n_per_bin)
-    n_tot = len(ptot)
+        ptot = centres
+        counts = np.full(nb, n_per_bin, np.int64)
+        weight = np.array([a / area_tot / n_per_bin * n0 for a in areas])
+    n_tot = int(counts.sum())
     if inp_distr == 2:
         E_inj = T_or_E * KEV
-        p = math.sqrt(2 * m * E_inj) if E_inj / E0 < E_REL_PT else math.sqrt(E_inj**2 - E0**2) / CL
-        ptot = np.full(n_pts_inj, p)
-        weight = np.full(n_pts_inj, n0 / n_tot)
-    return np.asarray(ptot, float), np.asarray(weight, float)
+        pm = math.sqrt(2 * m * E_inj) if E_inj / E0 < E_REL_PT else math.sqrt(E_inj**2 - E0**2) / CL
+        ptot, weight, counts = np.array([pm]), np.array([n0 / n_tot]), np.array([n_pts_inj], np.int64)
+    return np.asarray(ptot, float), np.asarray(weight, float), counts
+
+
+def set_inj_dist(inj_weight: bool, n_pts_inj: int, inp_distr: int, T_or_E: float, m: float, n0: float,
+                 compat_zero_first=False):
+    """initializers.jl:1251-1328, one entry per particle. Returns (ptot[n], weight[n])."""
+    ptot, weight, counts = inj_bins(inj_weight, n_pts_inj, inp_distr, T_or_E, m, n0, compat_zero_first)
+    return np.repeat(ptot, counts), np.repeat(weight, counts)
+
+
+# McsInjection.mode (include/mcs.h)
+INJ_UPSTREAM, INJ_FASTPUSH_NONREL, INJ_FASTPUSH_REL = 0, 1, 2
+INJ_PERM_STRIDE = 64
+
+
+@dataclass
+class InjectionSpec:
+    """init_pop in run-length form: everything a generator (host mirror, oracle, CUDA) needs to emit the population.
+    Per bin: momentum, weight, count and the two ends (lo, hi) of the range the x-velocity of a fast-pushed particle is
+    drawn from (TriangularDist(lo, hi, hi), initializers.jl:1100-1125), `gfac` = gamma_pf * m.  All per-bin values are
+    computed here, on the host, so a generator only does sqrt / add / mul / div per particle (bit-reproducible)."""
+    mode: int
+    bin_ptot: np.ndarray
+    bin_weight: np.ndarray
+    bin_count: np.ndarray
+    bin_lo: np.ndarray
+    bin_hi: np.ndarray
+    bin_gfac: np.ndarray
+    x_cm: float
+    grid: int
+    u_stop: float
+    pxx_flux: np.ndarray
+    pxz_flux: np.ndarray
+    energy_flux: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return int(self.bin_count.sum())
+
+    @property
+    def weight_running(self) -> float:
+        nz = np.nonzero(self.bin_count)[0]
+        return float(self.bin_weight[nz[0]]) if len(nz) else 0.0
 
 
 @dataclass
 class InitPop:
-    pop: dict           # weight, ptot_pf, pb_pf, x_cm, grid, phi_rad (arrays of n_pts_use)
-    pxx_flux: np.ndarray  # fast-push prefill (F_update!), else zeros
+    pop: dict
+    pxx_flux: np.ndarray
     pxz_flux: np.ndarray
     energy_flux: np.ndarray
     weight_running: float
 
 
-def init_pop(run: Run, prof: Profile, i_ion: int, rng: np.random.Generator, shuffle: bool = False) -> InitPop:
-    """init_pop (initializers.jl:977-1134), F_update! (:1157-1223) and the phase draw of
-    assign_particle_properties_to_population! (ion_init.jl:51). `rng` replaces Random.Xoshiro of
-    main_loops.jl:120-121 (host side, outside the replaced region): one uniform block for pb (or one
-    triangular draw per particle), then one uniform block for phi."""
+def injection_spec(run: Run, prof: Profile, i_ion: int) -> InjectionSpec:
+    """The deterministic part of init_pop (initializers.jl:977-1134) and F_update! (:1157-1223)."""
     inp = run.inp
     sp = run.species[i_ion - 1]
     m, ng = sp.mass, run.n_grid
     pxx, pxz, efl = np.zeros(ng), np.zeros(ng), np.zeros(ng)
     if not inp.fast_upstream_transport:
         T_or_E = sp.T if inp.input_distribution == 1 else inp.injection_energy_keV
-        ptot, w = set_inj_dist(inp.injection_weights, inp.n_pts_inj, inp.input_distribution, T_or_E, m, sp.n0,
-                               inp.compat_zero_first_particle)
-        n = len(ptot)
-        pb = ptot * 2 * (rng.random(n) - 0.5)
-        x = np.full(n, run.x_grid_start - 10 * run.rg0 * inp.gyrofactor)
-        grid = np.zeros(n, np.int64)
+        ptot, w, cnt = inj_bins(inp.injection_weights, inp.n_pts_inj, inp.input_distribution, T_or_E, m, sp.n0,
+                                inp.compat_zero_first_particle)
+        z = np.zeros(len(ptot))
+        return InjectionSpec(INJ_UPSTREAM, ptot, w, cnt, z, z.copy(), np.full(len(ptot), m),
+                             run.x_grid_start - 10 * run.rg0 * inp.gyrofactor, 0, 0.0, pxx, pxz, efl)
+    if inp.input_distribution > 1:
+        raise ValueError("fast push will only work with thermal input distr.")
+    x_stop_rg = inp.proton_fast_transport_stop
+    i_stop = int(np.argmax(prof.x_grid_rg > x_stop_rg)) - 1
+    rel = run.beta0 >= BETA_REL_FL
+    dr = run.u0 / prof.ux_sk[i_stop]
+    if rel:
+        dr *= run.gam0 / prof.gam_sf[i_stop]
+    G = 5.0 / 3.0
+    temp_ratio = dr**G / dr
+    if KB * sp.T * temp_ratio > 4 * m * CL**2 * E_REL_PT:
+        raise ValueError("Fast push cannot work: thermal particles become mildly relativistic.")
+    if i_ion == 1:  # F_update!
+        P0 = sum(s.n0 * s.T for s in run.species) * KB
+        rho0 = sum(s.n0 * s.mass for s in run.species)
+        Xi = G / (G - 1)
+        for i in range(1, i_stop + 1):
+            uc, gc = prof.ux_sk[i], prof.gam_sf[i]
+            bc = uc / CL
+            gb = gc * bc
+            d = (run.gam0 * run.u0) / (gc * uc)
+            rho, P = rho0 * d, P0 * d**G
+            if not rel:
+                Fp = rho * uc**2 * (1 + bc**2) + P * (1 + Xi * bc**2)
+                Fe = rho / 2 * uc**3 * (1 + 1.25 * bc**2) + P * uc * Xi * (1 + bc**2)
+            else:
+                e = rho * CL**2
+                Fp = P + gb**2 * (e + Xi * P)
+                Fe = gb * gc * CL * (e + Xi * P) - gb * CL * e
+            pxx[i - 1], pxz[i - 1], efl[i - 1] = Fp, 0.0, Fe
+    ptot, w, cnt = inj_bins(inp.injection_weights, inp.n_pts_inj, inp.input_distribution, sp.T * temp_ratio, m,
+                            sp.n0, inp.compat_zero_first_particle)
+    u = prof.ux_sk[i_stop]
+    bu = u / CL
+    if rel:
+        gpf = np.hypot(1.0, ptot / (m * CL))
+        bpf = np.sqrt(1 - 1 / gpf**2)
+        lo = np.abs((bu - bpf) / (1 - bu * bpf))
+        hi = np.abs((bu + bpf) / (1 + bu * bpf))
+        gfac = gpf * m
     else:
-        if inp.input_distribution > 1:
-            raise ValueError("fast push will only work with thermal input distr.")
-        x_stop_rg = inp.proton_fast_transport_stop
-        i_stop = int(np.argmax(prof.x_grid_rg > x_stop_rg)) - 1
-        rel = run.beta0 >= BETA_REL_FL
-        dr = run.u0 / prof.ux_sk[i_stop]
-        if rel:
-            dr *= run.gam0 / prof.gam_sf[i_stop]
-        G = 5.0 / 3.0
-        temp_ratio = dr**G / dr
-        if KB * sp.T * temp_ratio > 4 * m * CL**2 * E_REL_PT:
-            raise ValueError("Fast push cannot work: thermal particles become mildly relativistic.")
-        if i_ion == 1:  # F_update!
-            P0 = sum(s.n0 * s.T for s in run.species) * KB
-            rho0 = sum(s.n0 * s.mass for s in run.species)
-            Xi = G / (G - 1)
-            for i in range(1, i_stop + 1):
-                uc, gc = prof.ux_sk[i], prof.gam_sf[i]
-                bc = uc / CL
-                gb = gc * bc
-                d = (run.gam0 * run.u0) / (gc * uc)
-                rho, P = rho0 * d, P0 * d**G
-                if not rel:
-                    Fp = rho * uc**2 * (1 + bc**2) + P * (1 + Xi * bc**2)
-                    Fe = rho / 2 * uc**3 * (1 + 1.25 * bc**2) + P * uc * Xi * (1 + bc**2)
-                else:
-                    e = rho * CL**2
-                    Fp = P + gb**2 * (e + Xi * P)
-                    Fe = gb * gc * CL * (e + Xi * P) - gb * CL * e
-                pxx[i - 1], pxz[i - 1], efl[i - 1] = Fp, 0.0, Fe
-        ptot, w = set_inj_dist(inp.injection_weights, inp.n_pts_inj, inp.input_distribution, sp.T * temp_ratio, m,
-                               sp.n0, inp.compat_zero_first_particle)
-        n = len(ptot)
-        x = np.full(n, x_stop_rg * run.rg0)
-        grid = np.full(n, i_stop, np.int64)
-        u = prof.ux_sk[i_stop]
-        bu = u / CL
-        r = rng.random(n)
+        vt = ptot / m
+        lo, hi = np.abs(u - vt), np.abs(u + vt)
+        gfac = np.full(len(ptot), 1.0 * m)
+    return InjectionSpec(INJ_FASTPUSH_REL if rel else INJ_FASTPUSH_NONREL, ptot, w, cnt, lo, hi, gfac,
+                         x_stop_rg * run.rg0, i_stop, float(u), pxx, pxz, efl)
+
+
+def injection_permutation(n: int, stride: int = INJ_PERM_STRIDE) -> np.ndarray:
+    """Slot -> origin index.  The reference orders the injected particles by momentum bin.  Sharding contiguous index
+    blocks over GPUs then gives rank 0 the slow half and the last rank the fast half of the Maxwellian, i.e.
+    unequal numbers of survivors per rank.  A fixed permutation (independent of the rank count) removes that; the order
+    only decides which RNG counter a particle gets.  The permutation is `stride` strided sub-sequences laid end to end
+    (indices 0,64,128,... then 1,65,...): any block of n/W particles (W = 1,2,4,8,...,64 ranks) is a fair sample of the
+    Maxwellian AND stays momentum-sorted inside, which keeps the lanes of a warp on similar trajectories (a random
+    shuffle costs 3 % on one GPU)."""
+    return np.concatenate([np.arange(k, n, stride) for k in range(stride)]) if n else np.zeros(0, np.int64)
+
+
+def expand_injection(spec: InjectionSpec, rng, shuffle: bool = False) -> InitPop:
+    """Host generator: one uniform block for pb (or one triangular draw per particle), then one uniform block for phi
+    (ion_init.jl:51).  `rng.random(n)` is numpy's Generator or PhiloxInjectionRng (the stream the oracle and the CUDA
+    generator use)."""
+    cnt = spec.bin_count
+    n = spec.n
+    ptot, w = np.repeat(spec.bin_ptot, cnt), np.repeat(spec.bin_weight, cnt)
+    r = rng.random(n)
+    if spec.mode == INJ_UPSTREAM:
+        pb = ptot * 2 * (r - 0.5)
+    else:
+        lo, hi, gfac = np.repeat(spec.bin_lo, cnt), np.repeat(spec.bin_hi, cnt), np.repeat(spec.bin_gfac, cnt)
         # TriangularDist(a, b, b) sample = a + (b - a) sqrt(U)   (SURVEY 8c)
-        if rel:
-            gpf = np.hypot(1.0, ptot / (m * CL))
-            bpf = np.sqrt(1 - 1 / gpf**2)
-            bmin = np.abs((bu - bpf) / (1 - bu * bpf))
-            bmax = np.abs((bu + bpf) / (1 + bu * bpf))
-            bx = bmin + (bmax - bmin) * np.sqrt(r)
-            vx_pf = (bx - bu) / (1 - bx * bu) * CL
-            pb = gpf * m * vx_pf
+        vx = lo + (hi - lo) * np.sqrt(r)
+        if spec.mode == INJ_FASTPUSH_REL:
+            bu = spec.u_stop / CL
+            vx_pf = (vx - bu) / (1 - vx * bu) * CL
+            pb = gfac * vx_pf
         else:
-            vt = ptot / m
-            vmin, vmax = np.abs(u - vt), np.abs(u + vt)
-            vx_sf = vmin + (vmax - vmin) * np.sqrt(r)
-            pb = 1.0 * m * (vx_sf - u)
+            pb = gfac * (vx - spec.u_stop)
+    x = np.full(n, spec.x_cm)
+    grid = np.full(n, spec.grid, np.int64)
     phi = 2 * math.pi * rng.random(n)
     if shuffle:
-        # The reference orders the injected particles by momentum bin.  Sharding contiguous index blocks over GPUs
-        # (SURVEY 8e) then gives rank 0 the slow half and the last rank the fast half of the Maxwellian, i.e. unequal
-        # numbers of survivors per rank.  A fixed permutation (independent of the rank count) removes that; the order
-        # only decides which RNG counter a particle gets.  The permutation is 64 strided sub-sequences laid end to end
-        # (indices 0,64,128,... then 1,65,...): any block of n/W particles (W = 1,2,4,8,...,64 ranks) is a fair sample
-        # of the Maxwellian AND stays momentum-sorted inside, which keeps the lanes of a warp on similar trajectories
-        # (a random shuffle costs 3 % on one GPU).
-        perm = np.concatenate([np.arange(k, n, 64) for k in range(64)])
+        perm = injection_permutation(n)
         w, ptot, pb, x, grid, phi = w[perm], ptot[perm], pb[perm], x[perm], grid[perm], phi[perm]
     pop = dict(weight=w, ptot_pf=ptot, pb_pf=pb, x_cm=x, grid=grid, phi_rad=phi)
-    return InitPop(pop=pop, pxx_flux=pxx, pxz_flux=pxz, energy_flux=efl, weight_running=float(w[0]) if n else 0.0)
+    return InitPop(pop=pop, pxx_flux=spec.pxx_flux, pxz_flux=spec.pxz_flux, energy_flux=spec.energy_flux,
+                   weight_running=spec.weight_running)
+
+
+def init_pop(run: Run, prof: Profile, i_ion: int, rng, shuffle: bool = False) -> InitPop:
+    """init_pop (initializers.jl:977-1134), F_update! (:1157-1223) and the phase draw of
+    assign_particle_properties_to_population! (ion_init.jl:51). `rng` replaces Random.Xoshiro of
+    main_loops.jl:120-121 (host side, outside the replaced region)."""
+    return expand_injection(injection_spec(run, prof, i_ion), rng, shuffle)
+
+
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Philox4x32-10 (Salmon et al. 2011) on numpy uint32 arrays; the generator of the library (include/mcs.h)."""
+    c = [np.asarray(v, np.uint64) & np.uint64(0xFFFFFFFF) for v in np.broadcast_arrays(c0, c1, c2, c3)]
+    m32 = np.uint64(0xFFFFFFFF)
+    for r in range(10):
+        p0, p1 = _PHILOX_M0 * c[0], _PHILOX_M1 * c[2]
+        ka, kb = np.uint64((k0 + r * _PHILOX_W0) & 0xFFFFFFFF), np.uint64((k1 + r * _PHILOX_W1) & 0xFFFFFFFF)
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ ka, p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ kb, p0 & m32]
+    return c
+
+
+class PhiloxInjectionRng:
+    """The uniforms the library's generators use for particle j of (iteration, ion): Philox counter
+    (0, j, i_ion << 16, i_iter) — pcut field 0, which the transport never uses — key = seed; first `random(n)` call returns
+    the first 53-bit uniform of each block (pitch angle), the second call the second (phase)."""
+
+    def __init__(self, seed: int, i_iter: int, i_ion: int):
+        self.k0, self.k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+        self.c2, self.c3 = (i_ion << 16) & 0xFFFFFFFF, i_iter & 0xFFFFFFFF
+        self._calls = 0
+        self._blk = None
+
+    def random(self, n: int) -> np.ndarray:
+        if self._blk is None or len(self._blk[0]) != n:
+            j = np.arange(n, dtype=np.uint64)
+            self._blk = philox4x32_10(0, j, self.c2, self.c3, self.k0, self.k1)
+            self._calls = 0
+        o = self._blk
+        lo, hi = (o[0], o[1]) if self._calls == 0 else (o[2], o[3])
+        self._calls += 1
+        return (((hi << np.uint64(32)) | lo) >> np.uint64(11)).astype(np.float64) * 2.0**-53
 
 
 def synthetic_precursor(run: Run, r_sub: float = 3.0, scale_rg: float = 5.0) -> Profile:

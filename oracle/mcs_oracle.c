@@ -138,6 +138,8 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+static double u53(uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53; }
+
 static double rng_uniform(Rng* g) {
     if (g->mode == MCS_RNG_REPLAY) {
         if (g->n >= g->rn) { g->exhausted = 1; g->n++; return 0.5; }
@@ -933,6 +935,56 @@ int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies*
         P->acctime[i] = pop->acctime_sec ? pop->acctime_sec[i] : 0.0;
         P->tcut[i] = pop->tcut ? pop->tcut[i] : 1;
         if (P->grid[i] < 0 || P->grid[i] > h->n_grid + 1) return fail(MCS_ERR_ARG, "grid index out of range");
+    }
+    h->have_ion = 1;
+    return MCS_OK;
+}
+
+/* init_pop in run-length form (include/mcs.h McsInjection; initializers.jl:977-1134, ion_init.jl:29-53) */
+static int64_t inj_origin(int64_t s, int64_t n, int64_t K) {
+    if (K <= 0) return s;
+    int64_t a = n / K, b = n % K; /* the first b sub-sequences hold a+1 particles, the rest a */
+    if (s < b * (a + 1)) return s / (a + 1) + K * (s % (a + 1));
+    s -= b * (a + 1);
+    return (b + s / a) + K * (s % a);
+}
+int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies* sp, int64_t first_global,
+                           int64_t n_local, const McsInjection* inj) {
+    if (!h || !sp || !inj) return fail(MCS_ERR_ARG, "null argument");
+    if (!h->have_profile) return fail(MCS_ERR_STATE, "mcs_set_profile first");
+    if (i_ion < 1 || i_ion > h->cfg.n_ions) return fail(MCS_ERR_ARG, "i_ion out of range");
+    if (inj->n_bins < 1 || !inj->bin_ptot || !inj->bin_weight || !inj->bin_start) return fail(MCS_ERR_ARG, "injection bins missing");
+    if (inj->mode < 0 || inj->mode > 2) return fail(MCS_ERR_ARG, "injection mode");
+    if (inj->mode != MCS_INJ_UPSTREAM && (!inj->bin_lo || !inj->bin_hi || !inj->bin_gfac)) return fail(MCS_ERR_ARG, "fast-push bins missing");
+    int64_t n_total = inj->bin_start[inj->n_bins];
+    if (n_local < 0 || first_global < 0 || first_global + n_local > n_total) return fail(MCS_ERR_ARG, "shard outside the population");
+    if (n_local > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "n_pts exceeds n_pts_max");
+    if (inj->grid < 0 || inj->grid > h->n_grid + 1) return fail(MCS_ERR_ARG, "grid index out of range");
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->i_pcut = 0;
+    h->n_use = n_local; h->first_global = first_global; h->n_saved_last = 0;
+    zero_ion_tallies(h);
+    Pop* P = &h->cur;
+    const uint32_t key[2] = {(uint32_t)h->cfg.seed, (uint32_t)(h->cfg.seed >> 32)};
+    const double bu = inj->u_stop / h->cfg.c_cms;
+    for (int64_t i = 0; i < n_local; i++) {
+        int64_t j = inj_origin(first_global + i, n_total, inj->perm_stride);
+        int lo = 0, hi = inj->n_bins; /* bin_start[lo] <= j < bin_start[hi] */
+        while (hi - lo > 1) { int mid = (lo + hi) / 2; if (inj->bin_start[mid] <= j) lo = mid; else hi = mid; }
+        const uint32_t ctr[4] = {0u, (uint32_t)j, (uint32_t)i_ion << 16, (uint32_t)i_iter};
+        uint32_t o[4];
+        philox4x32_10(ctr, key, o);
+        double u1 = u53(o[1], o[0]), u2 = u53(o[3], o[2]);
+        double ptot = inj->bin_ptot[lo], pb;
+        if (inj->mode == MCS_INJ_UPSTREAM) pb = (ptot * 2) * (u1 - 0.5);
+        else {
+            double vx = inj->bin_lo[lo] + (inj->bin_hi[lo] - inj->bin_lo[lo]) * sqrt(u1);
+            if (inj->mode == MCS_INJ_FASTPUSH_REL) pb = inj->bin_gfac[lo] * ((vx - bu) / (1 - vx * bu) * h->cfg.c_cms);
+            else pb = inj->bin_gfac[lo] * (vx - inj->u_stop);
+        }
+        P->weight[i] = inj->bin_weight[lo]; P->ptot[i] = ptot; P->pb[i] = pb; P->x[i] = inj->x_cm; P->grid[i] = inj->grid;
+        P->phi[i] = TWO_PI * u2;
+        P->down[i] = 0; P->inj[i] = 0; P->xn_per[i] = h->cfg.xn_per_fine; P->prp_x[i] = h->cfg.x_grid_stop;
+        P->acctime[i] = 0.0; P->tcut[i] = 1;
     }
     h->have_ion = 1;
     return MCS_OK;
