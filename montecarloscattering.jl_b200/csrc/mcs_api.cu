@@ -102,6 +102,7 @@ struct McsHandle {
     int ng = 0, M = 0, T = 0;
     long long n_use = 0, first_global = 0, n_saved_last = 0, n_saved_global_last = 0;
     // device buffers
+    double* d_boost = nullptr; // 3 arrays of (ng+2): ux/ut, uz/ut, ux*uz/ut^2
     double* d_grid = nullptr;  // 10 arrays of (ng+2): xg ux uz ut gsf gef bt sinth costh (bef unused) + tcuts(NA_C)
     double* d_zone = nullptr;  // eps_target, recv_pool [ng] each
     PopPtrs pop[3];            // cur, saved, next
@@ -162,7 +163,7 @@ extern "C" int mcs_destroy(McsHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    cudaFree(h->d_grid); cudaFree(h->d_zone);
+    cudaFree(h->d_grid); cudaFree(h->d_boost); cudaFree(h->d_zone);
     for (auto& p : h->pop) pop_free(p);
     cudaFree(h->d_l_save); cudaFree(h->d_fate); cudaFree(h->d_helix); cudaFree(h->d_retro); cudaFree(h->d_draws);
     cudaFree(h->d_saved_idx); cudaFree(h->d_block_off); cudaFree(h->d_total); cudaFree(h->d_block_cnt);
@@ -225,6 +226,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     const int ng = h->ng, ng2 = ng + 2;
     const long long N = cfg->n_pts_max;
     CUA(cudaMalloc(&h->d_grid, (size_t)(9 * ng2 + MCS_NA_C) * 8));
+    CUA(cudaMalloc(&h->d_boost, (size_t)3 * ng2 * 8));
     CUA(cudaMalloc(&h->d_zone, (size_t)2 * ng * 8));
     for (auto& p : h->pop) TRY(pop_alloc(p, N));
     CUA(cudaMalloc(&h->d_l_save, (size_t)N)); CUA(cudaMalloc(&h->d_fate, (size_t)N * 4)); CUA(cudaMalloc(&h->d_helix, (size_t)N * 4));
@@ -291,6 +293,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     double* g = h->d_grid;
     P.xg = g; P.ux = g + ng2; P.uz = g + 2 * ng2; P.ut = g + 3 * ng2; P.gsf = g + 4 * ng2; P.gef = g + 5 * ng2;
     P.bt = g + 6 * ng2; P.sinth = g + 7 * ng2; P.costh = g + 8 * ng2; P.tcuts = g + 9 * ng2;
+    P.rxt = h->d_boost; P.rzt = h->d_boost + ng2; P.crt = h->d_boost + 2 * ng2;
     P.eps_target = h->d_zone; P.recv_pool = h->d_zone + ng;
     P.l_save = h->d_l_save; P.fate = h->d_fate; P.helix = h->d_helix; P.retro = h->d_retro; P.draws = h->d_draws;
     TallyPtrs& t = P.t;
@@ -351,6 +354,13 @@ extern "C" int mcs_set_profile(McsHandle* h, int32_t n_grid, const double* xg, c
     }
     if (eps_target) memcpy(&buf[(size_t)9 * ng2], eps_target, (size_t)h->ng * 8);
     if (recv_pool) memcpy(&buf[(size_t)9 * ng2 + h->ng], recv_pool, (size_t)h->ng * 8);
+    std::vector<double> boost((size_t)3 * ng2);
+    for (int i = 0; i < ng2; i++) {  // transformers.jl:553-560: the same three quotients for every particle entering zone i
+        boost[i] = ux[i] / ut[i];
+        boost[(size_t)ng2 + i] = uz[i] / ut[i];
+        boost[(size_t)2 * ng2 + i] = ux[i] * uz[i] / (ut[i] * ut[i]);
+    }
+    CU(cudaMemcpyAsync(h->d_boost, boost.data(), (size_t)3 * ng2 * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_grid, buf.data(), (size_t)9 * ng2 * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_zone, &buf[(size_t)9 * ng2], (size_t)2 * h->ng * 8, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));

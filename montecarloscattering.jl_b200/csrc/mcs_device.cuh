@@ -35,6 +35,12 @@
 #ifndef MCS_PARK_T
 #define MCS_PARK_T 16     // lanes that must be waiting (parked or refillable) before the warp leaves the fast loop
 #endif
+#ifndef MCS_PSP_DEBT
+#define MCS_PSP_DEBT 256  // lane-iterations of waiting after which the pending boosts of a warp are served (fast loop)
+#endif
+#ifndef MCS_PSP_NUM
+#define MCS_PSP_NUM 2
+#endif
 #ifndef MCS_FAST_MAX
 #define MCS_FAST_MAX 256  // safety bound on consecutive fast passes
 #endif
@@ -115,6 +121,7 @@ struct DevParams {
     long long first_global, n_use;
     // grid arrays (n_grid+2) and per-zone tables
     const double *xg, *ux, *uz, *ut, *gsf, *gef, *bt, *sinth, *costh, *tcuts;
+    const double *rxt, *rzt, *crt;  // per zone: ux/ut, uz/ut, ux*uz/ut^2 (the direction factors of transform_p_PSP)
     const double *eps_target, *recv_pool;  // [n_grid]
     PopPtrs cur, saved;
     uint8_t* l_save;
@@ -324,16 +331,15 @@ struct ColdIO {
 // transformers.jl:523-607; zone `io` -> shock frame -> zone `in`
 __device__ __noinline__ Mom transform_p_PSP(const DevParams& P, int io, int in, Mom mi) {
     double pb = mi.pb, pperp = mi.pperp, gam_pf = mi.gam_pf, phi = mi.phi;
-    double ux_o = P.ux[io], uz_o = P.uz[io], ut_o = P.ut[io], gsf_o = P.gsf[io], bcos_o = P.costh[io],
-           bsin_o = P.sinth[io];
-    double ux = P.ux[in], uz = P.uz[in], ut = P.ut[in], gsf = P.gsf[in], bcos = P.costh[in], bsin = P.sinth[in];
+    double ux_o = P.ux[io], uz_o = P.uz[io], gsf_o = P.gsf[io], bcos_o = P.costh[io], bsin_o = P.sinth[io];
+    double ux = P.ux[in], uz = P.uz[in], gsf = P.gsf[in], bcos = P.costh[in], bsin = P.sinth[in];
     double sp, cp;
     sincos(phi + HALF_PI, &sp, &cp);
     double p_p_cos = pperp * cp;
     double fx = pb * bcos_o - p_p_cos * bsin_o;
     double fy = pperp * sp;
     double fz = pb * bsin_o + p_p_cos * bcos_o;
-    double rxo = ux_o / ut_o, rzo = uz_o / ut_o, cro = ux_o * uz_o / (ut_o * ut_o);
+    double rxo = P.rxt[io], rzo = P.rzt[io], cro = P.crt[io];  // ux/ut, uz/ut, ux*uz/ut^2 tabulated by mcs_set_profile
     double sx = ((gsf_o - 1) * (rxo * rxo) + 1) * fx + (gsf_o - 1) * cro * fz + gsf_o * gam_pf * P.m * ux_o;
     double sy = fy;
     double sz = (gsf_o - 1) * cro * fx + ((gsf_o - 1) * (rzo * rzo) + 1) * fz + gsf_o * gam_pf * P.m * uz_o;
@@ -341,7 +347,7 @@ __device__ __noinline__ Mom transform_p_PSP(const DevParams& P, int io, int in, 
     double pb_sk = sx * bcos + sz * bsin;
     if (ptot_sk < fabs(pb_sk)) count(P, CNT_W_PPERP);
     double gam_sk = hypot(ptot_sk / P.mc, 1.0);
-    double rx = ux / ut, rz = uz / ut, cr = ux * uz / (ut * ut);
+    double rx = P.rxt[in], rz = P.rzt[in], cr = P.crt[in];
     double nx = ((gsf - 1) * (rx * rx) + 1) * sx + (gsf - 1) * cr * sz - gsf * gam_sk * P.m * ux;
     double ny = sy;
     double nz = (gsf - 1) * cr * sx + ((gsf - 1) * (rz * rz) + 1) * sz - gsf * gam_sk * P.m * uz;
@@ -1119,32 +1125,27 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         // nothing and PARKS; when MCS_PARK_T lanes are waiting the warp goes round the outer loop once and the
         // general pass serves all of them together.  Per particle the sequence of operations is unchanged.
         if (fast_ok) {
+            bool need_psp = false;  // the lane stands at a zone change that needs a boost and waits for company (below)
+            int psp_debt = 0;       // lane-iterations spent waiting since the last batch of boosts (warp-uniform)
             for (int it = 0; it < MCS_FAST_MAX; it++) {
                 uint32_t fev = 0;  // crossing event produced by this fast pass
-                if (ip >= 0 && !parked) {
+                if (ip >= 0 && !parked && !need_psp) {
                     bool park = (helix >= P.helix_cap) | (i_return == 1) | (xsel > 1) |
                                 (P.energy_transfer_frac > 0 && !inj && x_old_le0 && i_grid_old != i_grid) |
                                 (ptot > P.pmax_cutoff) | (inj && x < P.feb_up) | (P.age_max > 0 && acct > P.age_max);
                     if (i_grid != iz && !park) {
-                        // Code Block 3 zone change (particle_loop.jl:186-228); the boost is an out-of-line call
-                        const int iz_old = iz;
-                        iz = i_grid;
-                        const double ux_n = P.ux[iz];
-                        gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
-                        gd = 1 / (P.zz * P.bt[iz]);
-                        if (ux_n != ux) {
-                            ux = ux_n;
-                            Mom mi;
-                            mi.ptot = ptot; mi.pb = pb; mi.pperp = pperp; mi.gam_pf = gam_pf; mi.phi = phi;
-                            const Mom mo = transform_p_PSP(P, iz_old, iz, mi);
-                            ptot = mo.ptot; pb = mo.pb; pperp = mo.pperp; gam_pf = mo.gam_pf; phi = mo.phi;
-                            gr = pperp * P.c * gd;
-                            grt = ptot * P.c * gd;
-                            inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
-                            // the boosted momentum may now exceed a cut-off: let the general pass decide
-                            park = (ptot > P.pmax_cutoff) | (down && ptot > P.pcut);
+                        // Code Block 3 zone change (particle_loop.jl:186-228).  Without a change of flow speed it is a
+                        // reload of the zone's constants; with one, the momentum must be boosted (transform_p_PSP, ~350
+                        // instructions out of line).  In a smoothed precursor about one lane per iteration needs that,
+                        // so boosts are served in batches after the pass instead of one lane at a time.
+                        if (P.ux[i_grid] != ux) need_psp = true;
+                        else {
+                            iz = i_grid;
+                            gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                            gd = 1 / (P.zz * P.bt[iz]);
                         }
                     }
+                  if (!need_psp) {
                     double acct_n = acct;
                     if (down) {
                         acct_n = acct + t_step * gef;
@@ -1252,6 +1253,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         }
                     }
                     parked = park;
+                  }
                 }
                 {   // converged: queue the crossing events of this fast pass (state right after the move, as at point A)
                     const unsigned m = __ballot_sync(FULL, fev != 0u);
@@ -1270,6 +1272,36 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                         }
                     }
                 }
+                {   // converged: pending boosts.  Waiting costs idle lanes, serving costs the whole warp ~350 issue slots:
+                    // serve once the lanes have waited MCS_PSP_DEBT lane-iterations in total, or when fewer lanes run
+                    // than wait.
+                    const unsigned mp = __ballot_sync(FULL, need_psp);
+                    if (mp) {
+                        const int n_psp = __popc(mp);
+                        const int n_run = __popc(__ballot_sync(FULL, ip >= 0 && !parked && !need_psp));
+                        psp_debt += n_psp;
+                        if (psp_debt >= MCS_PSP_DEBT || MCS_PSP_NUM * n_psp >= n_run) {
+                            psp_debt = 0;
+                            if (need_psp) {
+                                need_psp = false;
+                                const int iz_old = iz;
+                                iz = i_grid;
+                                ux = P.ux[iz];
+                                gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
+                                gd = 1 / (P.zz * P.bt[iz]);
+                                Mom mi;
+                                mi.ptot = ptot; mi.pb = pb; mi.pperp = pperp; mi.gam_pf = gam_pf; mi.phi = phi;
+                                const Mom mo = transform_p_PSP(P, iz_old, iz, mi);
+                                ptot = mo.ptot; pb = mo.pb; pperp = mo.pperp; gam_pf = mo.gam_pf; phi = mo.phi;
+                                gr = pperp * P.c * gd;
+                                grt = ptot * P.c * gd;
+                                inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
+                                // the boosted momentum may now exceed a cut-off: let the general pass decide
+                                parked = (ptot > P.pmax_cutoff) | (down && ptot > P.pcut);
+                            }
+                        }
+                    }
+                }
                 MCS_SC(c_fast_iter++;)
                 const unsigned active = __ballot_sync(FULL, ip >= 0);
                 const unsigned waiting = __ballot_sync(FULL, (ip >= 0 && parked) || (ip < 0 && !queue_empty));
@@ -1277,6 +1309,7 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 if (n_wait > 0 && n_wait >= min(MCS_PARK_T, (3 * n_act + 3) >> 2)) break;
                 if (n_act == 0) break;
             }
+            if (need_psp) parked = true;  // left the loop with a boost pending: the general pass does the zone change
         } else {
             parked = true;
         }

@@ -6,7 +6,7 @@ N=${1:-100000}
 SKIP=${2:-5}
 TAG=${3:-prof}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 0 --n-per-pcut $N --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 0 --n-per-pcut $N --no-cpu-baseline --workload ${WORKLOAD:-planar}"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
