@@ -38,6 +38,9 @@
 #ifndef MCS_PSP_DEBT
 #define MCS_PSP_DEBT 256  // lane-iterations of waiting after which the pending boosts of a warp are served (fast loop)
 #endif
+#ifndef MCS_WAIT_DEBT
+#define MCS_WAIT_DEBT 1024  // total idle lane-iterations after which the warp leaves the fast loop to serve its waiting lanes
+#endif
 #ifndef MCS_PSP_NUM
 #define MCS_PSP_NUM 2
 #endif
@@ -1127,6 +1130,9 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         if (fast_ok) {
             bool need_psp = false;  // the lane stands at a zone change that needs a boost and waits for company (below)
             int psp_debt = 0;       // lane-iterations spent waiting since the last batch of boosts (warp-uniform)
+#if MCS_WAIT_DEBT > 0
+            int wait_debt = 0;
+#endif
             for (int it = 0; it < MCS_FAST_MAX; it++) {
                 uint32_t fev = 0;  // crossing event produced by this fast pass
                 if (ip >= 0 && !parked && !need_psp) {
@@ -1308,6 +1314,12 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 const int n_act = __popc(active), n_wait = __popc(waiting);
                 if (n_wait > 0 && n_wait >= min(MCS_PARK_T, (3 * n_act + 3) >> 2)) break;
                 if (n_act == 0) break;
+#if MCS_WAIT_DEBT > 0
+                // few lanes waiting for a long time cost as much as many lanes waiting briefly: also leave once the
+                // waiting lanes have idled MCS_WAIT_DEBT lane-iterations in total (short trajectories: many refills)
+                wait_debt += n_wait;
+                if (wait_debt >= MCS_WAIT_DEBT) break;
+#endif
             }
             if (need_psp) parked = true;  // left the loop with a boost pending: the general pass does the zone change
         } else {
