@@ -826,7 +826,8 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                     prp_x = P.cur.prp_x[ip]; acct = P.cur.acctime[ip]; phi = P.cur.phi[ip];
                     i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
                     down = P.cur.down[ip]; inj = P.cur.inj[ip];
-                    helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0; parked = true;
+                    helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0;
+                    parked = !fast_ok;  // a fresh particle needs nothing the fast loop cannot do
                     xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
                     gam_pf = hypot(1.0, ptot / P.mc);
                     gd = 1 / (P.zz * P.bt[i_grid]);
@@ -1119,6 +1120,9 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             qn -= 32;
         }
         parked = false;
+        // lanes whose particle just finished are refilled before the fast loop, not after it: they would idle through
+        // a whole residency (up to MCS_FAST_MAX iterations, a large share of a short trajectory)
+        if (fast_ok && __any_sync(FULL, ip < 0 && !queue_empty)) continue;
 
         // ---- FAST LOOP ------------------------------------------------------------------------------------------
         // The bare arithmetic of a pass runs at 8e10 steps/s on B200 when it is a tight loop (scatter_only_kernel);
