@@ -137,6 +137,15 @@ def main():
     ap.add_argument("--generate-in-library", action="store_true",
                     help="SURVEY 8(f2): hand init_pop to the library in run-length form instead of copying host arrays")
     a = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(obj) + "\n").encode())
+
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,7 +158,7 @@ def main():
         v, s_per_it, st = cpu_arm(a.workload, a.cpu_sample, max(a.steps, 1), min(a.warmup, 1), threads)
         run, _ = build_run(a.workload, a.cpu_sample)
         sample = f"{a.cpu_sample} particles per pcut (of {a.n_per_pcut}), full pcut ladder, {st} steps per iteration"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": min(a.warmup, 1), "ms_per_step": s_per_it * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -308,7 +317,7 @@ def main():
             v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads)
             out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
                                    "sample": f"{a.cpu_sample} particles per pcut, full pcut ladder, {st} steps, {s_it:.1f} s"}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
