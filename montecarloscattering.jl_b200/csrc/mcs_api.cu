@@ -290,6 +290,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
         }
     }
     P.key0 = (uint32_t)cfg->seed; P.key1 = (uint32_t)(cfg->seed >> 32);
+    for (int r = 0; r < 10; r++) { P.rk[2 * r] = P.key0 + (uint32_t)r * 0x9E3779B9u; P.rk[2 * r + 1] = P.key1 + (uint32_t)r * 0xBB67AE85u; }
     double* g = h->d_grid;
     P.xg = g; P.ux = g + ng2; P.uz = g + 2 * ng2; P.ut = g + 3 * ng2; P.gsf = g + 4 * ng2; P.gef = g + 5 * ng2;
     P.bt = g + 6 * ng2; P.sinth = g + 7 * ng2; P.costh = g + 8 * ng2; P.tcuts = g + 9 * ng2;
