@@ -317,6 +317,11 @@ def main():
             v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads)
             out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
                                    "sample": f"{a.cpu_sample} particles per pcut, full pcut ladder, {st} steps, {s_it:.1f} s"}
+            # the reference loop itself is serial (the threading directive at main_loops.jl:227 is a comment): one thread too
+            n1 = max(a.cpu_sample // 10, 200)
+            v1, s1, st1 = cpu_arm(a.workload, n1, 1, 0, 1)
+            out["cpu_baseline"]["single_thread"] = {"value": v1, "cores": 1,
+                                                    "sample": f"{n1} particles per pcut, {st1} steps, {s1:.1f} s"}
         emit(out)
     if dist is not None:
         dist.barrier()
