@@ -33,18 +33,32 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FLOP_PER_STEP = 185.0  # SURVEY.md 8d, Appendix D; restated in DESIGN.md
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE transport-kernel launch at 1e6 particles per pcut, from the
-# `ncu --set full` capture summarised in profiles/r01_v5_transport_kernel_summary.md (154.4 MB + 92.6 MB, launch 7 of 11).
-# Algorithmic bytes of that launch: 1e6 particles x (82 B in + 83 B out) = 165 MB; the rest is PSD / log atomics.
-NCU_DRAM_BYTES_PER_LAUNCH_1E6 = 247.0e6
+# roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE transport-kernel launch, read from the tracked
+# summary of the `ncu --set full` capture of this kernel on this workload (written by tools/ncu_summary.py --json from the
+# .ncu-rep; tools/profile.sh).  Reported only when the capture matches the workload and the particle count; else null.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 METRIC = "scattering_steps_per_sec"
 
 
-def build_run(workload: str, n_per_pcut: int):
+def measured_traffic(workload, n_per_pcut):
+    try:
+        rec = json.load(open(TRAFFIC_FILE))
+    except (OSError, ValueError):
+        return None, None
+    for r in rec.get("captures", []):
+        if r.get("workload") == workload and int(r.get("n_per_pcut", -1)) == int(n_per_pcut):
+            return (float(r["dram_bytes_read"]) + float(r["dram_bytes_write"]),
+                    f"profiles/r02_traffic.json: {r.get('source', '?')} (launch {r.get('launch', '?')}, "
+                    f"red sectors {r.get('lts_sectors_red')}, atom sectors {r.get('lts_sectors_atom')})")
+    return None, None
+
+
+def build_run(workload: str, n_per_pcut: int, pcuts: str = "bench"):
     from mcs_b200 import problem
     mk = {"planar": problem.planar_test_particle_input, "relativistic": problem.relativistic_input,
           "nonlinear": problem.nonlinear_input, "multi": problem.multi_species_input}[workload]
-    inp = mk(n_per_pcut)
+    kw = {"momentum_cutoffs": list(problem.DEFAULT_PCUTS)} if pcuts == "default" else {}
+    inp = mk(n_per_pcut, **kw)
     inp.num_iterations = 1
     run = problem.setup_run(inp)
     prof = problem.synthetic_precursor(run) if workload == "nonlinear" else run.profile
@@ -103,25 +117,84 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_arm(workload, sample_per_pcut, steps, warmup, threads):
+def cpu_arm(workload, sample_per_pcut, steps, warmup, threads, pcuts="bench", all_species=False):
     """The reference's CPU implementation of the path = the C restatement (oracle/), all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_engine
     from mcs_b200 import abi, driver
     lib = oracle_engine.load_oracle_library()
-    run, prof = build_run(workload, sample_per_pcut)
+    run, prof = build_run(workload, sample_per_pcut, pcuts)
     run.profile = prof
     e = abi.Engine(lib, driver.make_config(lib, run, threads=threads, na_cr=1000))
     tot_steps, tot_t = 0, 0.0
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        r = driver.main_loops(run, e, n_iters=1, want_psd=True, want_log=False, shuffle_population=True)[0][0]
+        res = driver.main_loops(run, e, n_iters=1, want_psd=True, want_log=False, shuffle_population=True,
+                                only_ions=None if all_species else [1])[0]
         dt = time.perf_counter() - t0
-        st = r["tallies"].stats["n_helix_steps"] + r["tallies"].stats["n_retro_steps"]
+        st = sum(r["tallies"].stats["n_helix_steps"] + r["tallies"].stats["n_retro_steps"] for r in res if r is not None)
         if it >= warmup:
             tot_steps += st
             tot_t += dt
     return tot_steps / tot_t, tot_t / max(steps, 1), tot_steps // max(steps, 1)
+
+
+class _Ranks:
+    """rank / world of this process for driver.main_loops (the library does the exchanges itself: device_comm=True)."""
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+
+def verify_multi_rank(lib, dist, rank, world, local_rank):
+    """Driver-visible evidence that the N-rank path computes what one rank computes: a 4000-particle x 4-pcut planar case
+    through mcs_run_ion on N ranks (NCCL inside the library, rebalancing split) and, on rank 0, the same global
+    population on a second single-rank handle.  Integers must be identical, flux sums agree to summation order."""
+    import torch
+    from mcs_b200 import abi, driver, problem
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    run = problem.setup_run(problem.planar_test_particle_input(4000, momentum_cutoffs=[0.01, 0.04, 0.06, 0.09]))
+    eng = abi.Engine(lib, driver.make_config(lib, run, na_cr=3_000_000, device=local_rank))
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(eng.comm_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    eng.comm_init(rank, world, bytes(uid.cpu().tolist()))
+    many = driver.main_loops(run, eng, n_iters=1, comm=_Ranks(rank, world), device_comm=True, want_log=False)[0][0]
+    eng.close()
+    out = None
+    if rank == 0:
+        e1 = abi.Engine(lib, driver.make_config(lib, run, na_cr=3_000_000, device=local_rank))
+        one = driver.main_loops(run, e1, n_iters=1, want_log=False)[0][0]
+        e1.close()
+        ta, tb = many["tallies"], one["tallies"]
+
+        def rel(x, y):
+            x, y = np.asarray(x, float), np.asarray(y, float)
+            sc = np.maximum(np.abs(x), np.abs(y))
+            m = sc > 0
+            return float((np.abs(x - y)[m] / sc[m]).max()) if m.any() else 0.0
+
+        out = {
+            "case": "planar 4000 particles x 4 pcuts, mcs_run_ion on N ranks (NCCL, rebalancing split) vs 1 rank",
+            "ranks": world,
+            "n_saved_equal": bool(np.array_equal(many["n_saved"], one["n_saved"])),
+            "n_used_equal": bool(np.array_equal(many["n_used"], one["n_used"])),
+            "n_fate_equal": ta.stats["n_fate"] == tb.stats["n_fate"],
+            "n_helix_steps_equal": ta.stats["n_helix_steps"] == tb.stats["n_helix_steps"]
+                                   and ta.stats["n_retro_steps"] == tb.stats["n_retro_steps"],
+            "num_crossings_equal": bool(np.array_equal(ta.num_crossings, tb.num_crossings)),
+            "psd_bitwise_equal": bool(np.array_equal(ta.psd, tb.psd)),
+            "max_rel_diff": {"pxx_flux": rel(ta.pxx_flux, tb.pxx_flux), "pxz_flux": rel(ta.pxz_flux, tb.pxz_flux),
+                             "energy_flux": rel(ta.energy_flux, tb.energy_flux), "psd": rel(ta.psd, tb.psd),
+                             "esc_psd_feb_downstream": rel(ta.esc_psd_feb_downstream, tb.esc_psd_feb_downstream)},
+            "n_saved": [int(v) for v in many["n_saved"]],
+        }
+        d = out["max_rel_diff"]
+        out["ok"] = bool(out["n_saved_equal"] and out["n_used_equal"] and out["n_fate_equal"] and out["n_helix_steps_equal"]
+                         and out["num_crossings_equal"] and max(d["pxx_flux"], d["pxz_flux"], d["energy_flux"]) < 1e-11
+                         and d["psd"] < 1e-10 and d["esc_psd_feb_downstream"] < 1e-10)
+    dist.barrier()
+    return out
 
 
 def main():
@@ -132,8 +205,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="planar", choices=["planar", "relativistic", "nonlinear", "multi"])
     ap.add_argument("--n-per-pcut", type=int, default=1_000_000)
+    ap.add_argument("--pcuts", default="bench", choices=["bench", "default"],
+                    help="bench: the workload's own ladder; default: the 45 cut-offs of the reference's mc_in.toml:84-130")
+    ap.add_argument("--all-species", action="store_true",
+                    help="multi workload: one step = all ion species of the iteration (p, He, e-) with the pool hand-over")
     ap.add_argument("--cpu-sample", type=int, default=10000, help="particles per pcut of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the N-rank vs 1-rank check that precedes a multi-GPU run")
     ap.add_argument("--generate-in-library", action="store_true",
                     help="SURVEY 8(f2): hand init_pop to the library in run-length form instead of copying host arrays")
     a = ap.parse_args()
@@ -146,17 +224,17 @@ def main():
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(obj) + "\n").encode())
 
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
+    all_species = a.all_species and a.workload == "multi"
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        v, s_per_it, st = cpu_arm(a.workload, a.cpu_sample, max(a.steps, 1), min(a.warmup, 1), threads)
-        run, _ = build_run(a.workload, a.cpu_sample)
+        v, s_per_it, st = cpu_arm(a.workload, a.cpu_sample, max(a.steps, 1), min(a.warmup, 1), threads, a.pcuts, all_species)
+        run, _ = build_run(a.workload, a.cpu_sample, a.pcuts)
         sample = f"{a.cpu_sample} particles per pcut (of {a.n_per_pcut}), full pcut ladder, {st} steps per iteration"
         emit(({
             "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps,
@@ -193,17 +271,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def allsum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        return float(t.item())
+    lib = mcs_b200.load_cuda_library()
+    verify = None
+    if world > 1 and not a.no_verify:
+        verify = verify_multi_rank(lib, dist, rank, world, local_rank)
 
     n_global = a.n_per_pcut * world
-    run, prof = build_run(a.workload, n_global)
+    run, prof = build_run(a.workload, n_global, a.pcuts)
     run.profile = prof
-    lib = mcs_b200.load_cuda_library()
     cfg = driver.make_config(lib, run, n_pts_cap=n_global + 8, na_cr=1_000_000, device=local_rank)
     eng = abi.Engine(lib, cfg)
     if world > 1:
@@ -213,34 +288,52 @@ def main():
         dist.broadcast(uid, 0)
         eng.comm_init(rank, world, bytes(uid.cpu().tolist()))
 
-    # host inputs of one step, in pinned memory (the population main_loops.jl hands to the particle loop)
-    spec = problem.injection_spec(run, prof, 1)
-    lo, hi = driver.shard_bounds(spec.n, rank, world)
-    pinned, pop = [], {}
-    if not a.generate_in_library:
-        ip = problem.expand_injection(spec, np.random.default_rng(0), shuffle=True)
-        for k, v in ip.pop.items():
-            t = torch.from_numpy(np.ascontiguousarray(v[lo:hi])).pin_memory()
-            pinned.append(t)
-            pop[k] = t.numpy()
+    # host inputs of one step, in pinned memory (the populations main_loops.jl hands to the particle loop)
+    ions = [i for i in range(1, run.n_ions + 1) if not (run.species[i - 1].n0 == 0 and run.inp.skip_zero_density_species)]
+    if not all_species:
+        ions = ions[:1]
     eps = problem.populate_eps_target(run, prof)
-    sp = driver.species_struct(run, 1)
-    p_hi = problem.pcut_hi(run.inp.en_pcut_hi, run.species[0].mass)
-    h2d = sum(v.nbytes for v in pop.values()) + 11 * (run.n_grid + 2) * 8
-    if a.generate_in_library:
-        h2d += 6 * 8 * len(spec.bin_ptot) + 8
+    pinned, per_ion, h2d = [], {}, 0
+    for i_ion in ions:
+        spec = problem.injection_spec(run, prof, i_ion)
+        lo, hi = driver.shard_bounds(spec.n, rank, world)
+        pop = {}
+        if not a.generate_in_library:
+            ip = problem.expand_injection(spec, np.random.default_rng(i_ion - 1), shuffle=True)
+            for k, v in ip.pop.items():
+                t = torch.from_numpy(np.ascontiguousarray(v[lo:hi])).pin_memory()
+                pinned.append(t)
+                pop[k] = t.numpy()
+        per_ion[i_ion] = dict(spec=spec, lo=lo, hi=hi, pop=pop, sp=driver.species_struct(run, i_ion),
+                              p_hi=problem.pcut_hi(run.inp.en_pcut_hi, run.species[i_ion - 1].mass))
+        h2d += sum(v.nbytes for v in pop.values()) + 11 * (run.n_grid + 2) * 8
+        if a.generate_in_library:
+            h2d += 6 * 8 * len(spec.bin_ptot) + 8
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    D2H_FIELDS = ("pxx_flux", "pxz_flux", "energy_flux", "psd", "num_crossings", "esc_psd_feb_upstream", "esc_psd_feb_downstream",
+                  "esc_energy_eff", "esc_num_eff", "weight_coupled", "spectra_coupled", "energy_transfer_pool")
 
     def one_step():
-        """The call sequence a Julia user makes per (iteration, ion): H2D, the device pcut loop, D2H."""
-        eng.set_profile(prof, eps, np.zeros(run.n_grid))
-        if a.generate_in_library:
-            eng.begin_ion_generate(1, 1, sp, spec, first_global=lo, n_local=hi - lo, shuffle=True)
-        else:
-            eng.begin_ion(1, 1, sp, pop, first_global=lo)
-        n_run, n_used, n_saved = eng.run_ion(run.pcuts, p_hi, run.inp.n_pts_pcut, run.inp.n_pts_pcut_hi)
-        t = eng.end_ion(want_psd=True, want_log=False)
-        return t, n_run
+        """The call sequence a Julia user makes per iteration: for each ion H2D, the device pcut loop, D2H; the energy pool
+        donated by the ions is handed to the next species (main_loops.jl:95-164)."""
+        pool = np.zeros(run.n_grid)
+        res = {}
+        for i_ion in ions:
+            d = per_ion[i_ion]
+            t0 = eng.timing()
+            eng.set_profile(prof, eps, pool.copy())
+            if a.generate_in_library:
+                eng.begin_ion_generate(1, i_ion, d["sp"], d["spec"], first_global=d["lo"], n_local=d["hi"] - d["lo"], shuffle=True)
+            else:
+                eng.begin_ion(1, i_ion, d["sp"], d["pop"], first_global=d["lo"])
+            n_run, n_used, n_saved = eng.run_ion(run.pcuts, d["p_hi"], run.inp.n_pts_pcut, run.inp.n_pts_pcut_hi)
+            t = eng.end_ion(want_psd=True, want_log=False)
+            pool = pool + t.energy_transfer_pool
+            t1 = eng.timing()
+            res[i_ion] = dict(t=t, n_run=n_run, steps=t.stats["n_helix_steps"] + t.stats["n_retro_steps"],
+                              loop_ms=t1["ion_loop_ms"] - t0["ion_loop_ms"], kern_ms=t1["transport_ms"] - t0["transport_ms"],
+                              d2h=sum(getattr(t, nm).nbytes for nm in D2H_FIELDS) + 8 * 8 + 24 * 8)
+        return res
 
     for _ in range(a.warmup):
         one_step()
@@ -249,24 +342,27 @@ def main():
     atomic_peak = eng.measure_atomic_peak(run.n_grid * (run.num_psd_mom_bins + 2) * (run.num_psd_theta_bins + 2))
     eng.timing(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    wall, steps_local, d2h, n_run = 0.0, 0, 0, 0
+    wall, res = 0.0, {}
+    sp_steps = {i: 0.0 for i in ions}
+    sp_ms = {i: 0.0 for i in ions}
     barrier()
     for _ in range(a.steps):
         flush.fill_(1)  # L2 flush between timed iterations (not timed)
         barrier()
         t0 = time.perf_counter()
-        t, n_run = one_step()
+        res = one_step()
         torch.cuda.synchronize()
         wall += time.perf_counter() - t0
-        steps_local = t.stats["n_helix_steps"] + t.stats["n_retro_steps"]  # already summed over ranks by the all-reduce
-        d2h = sum(getattr(t, nm).nbytes for nm in ("pxx_flux", "pxz_flux", "energy_flux", "psd", "num_crossings",
-                                                  "esc_psd_feb_upstream", "esc_psd_feb_downstream", "esc_energy_eff",
-                                                  "esc_num_eff", "weight_coupled", "spectra_coupled",
-                                                  "energy_transfer_pool")) + 8 * 8 + 24 * 8
+        for i in ions:
+            sp_steps[i] += res[i]["steps"]   # already summed over ranks by the all-reduce of mcs_end_ion
+            sp_ms[i] += res[i]["loop_ms"]
     barrier()
     clocks = sampler.stop() if sampler else None
     tm = eng.timing()
-    steps_per_iter = float(steps_local)  # global (counters are all-reduced in mcs_end_ion)
+    steps_total = float(sum(sp_steps.values()))      # global, all timed steps
+    steps_per_iter = steps_total / a.steps
+    d2h = sum(r["d2h"] for r in res.values())
+    n_run = max(r["n_run"] for r in res.values())
     dev_s = allmax(tm["ion_loop_ms"]) * 1e-3
     wall_s = allmax(wall)
     kern_s = allmax(tm["transport_ms"]) * 1e-3
@@ -279,23 +375,33 @@ def main():
         per_rank_steps = [float(x.item()) / a.steps for x in g]
         dist.all_gather(g, torch.tensor([float(tm["local_particles"])], dtype=torch.float64, device="cuda"))
         per_rank_particles = [float(x.item()) / a.steps for x in g]
-    value = steps_per_iter * a.steps / dev_s
-    e2e = steps_per_iter * a.steps / wall_s
+    value = steps_total / dev_s
+    e2e = steps_total / wall_s
     # dominant kernel: this rank's steps over this rank's kernel time
-    kern_steps_per_s = (steps_per_iter / world) * a.steps / kern_s
+    kern_steps_per_s = float(tm["local_steps"]) / (tm["transport_ms"] * 1e-3)
     achieved = kern_steps_per_s * FLOP_PER_STEP / 1e12
+    red_gops = float(tm["local_reds"]) / (tm["transport_ms"] * 1e-3) / 1e9
     launches = int(tm["transport_launches"] + tm["other_launches"])
+    traffic, traffic_src = measured_traffic(a.workload, a.n_per_pcut) if (a.pcuts == "bench" and not all_species) else (None, None)
 
     if rank == 0:
+        extra = {
+            "population": "generated in the library from the run-length injection list" if a.generate_in_library
+                          else "host arrays in pinned memory, copied every step",
+            "pcuts_run": int(n_run), "steps_per_iteration": int(steps_per_iter), "l2": "flushed between timed iterations",
+            "s_per_iteration_device": dev_s / a.steps, "s_per_iteration_e2e": wall_s / a.steps}
+        if all_species:
+            extra["step"] = "one iteration of ALL ion species (every pcut of each), energy pool handed from ions to electrons"
+            extra["species"] = {
+                f"ion{i}": {"aa": run.species[i - 1].aa, "n0": run.species[i - 1].n0, "electron": bool(run.species[i - 1].is_electron),
+                            "steps_per_iteration": int(sp_steps[i] / a.steps), "ms_per_iteration": sp_ms[i] / a.steps,
+                            "steps_per_s": sp_steps[i] / (sp_ms[i] * 1e-3) if sp_ms[i] > 0 else None,
+                            "pcuts_run": int(res[i]["n_run"])} for i in ions}
         out = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a.workload, run, a.n_per_pcut, {
-                "population": "generated in the library from the run-length injection list" if a.generate_in_library
-                              else "host arrays in pinned memory, copied every step",
-                "pcuts_run": int(n_run), "steps_per_iteration": int(steps_per_iter), "l2": "flushed between timed iterations",
-                "s_per_iteration_device": dev_s / a.steps, "s_per_iteration_e2e": wall_s / a.steps}),
+            "config": workload_config(a.workload, run, a.n_per_pcut, extra),
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": wall_s / a.steps * 1e3},
             "gpu_launches": launches, "per_rank_kernel_ms_per_step": per_rank_kernel_ms,
@@ -303,23 +409,28 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "transport_kernel<false>", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E6 * a.n_per_pcut / 1e6 if a.workload == "planar" else None,
-                         "traffic_source": "ncu --set full capture at 1e6 particles per pcut (profiles/), scaled by particle count",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "flop_per_step": FLOP_PER_STEP, "kernel_ms_per_launch": kern_s * 1e3 / max(tm["transport_launches"], 1),
                          "kernel_share_of_step": kern_s / dev_s,
                          "peak_source": "measured live: DFMA microbenchmark in libmcs_b200.so (MEASURED_PEAKS.json has no FP64 entry)",
                          "hot_path_ceiling_steps_per_s": scatter_peak,
                          "frac_of_hot_path_ceiling": kern_steps_per_s / scatter_peak if scatter_peak else None,
                          "hot_path_ceiling_source": "measured live: scatter_only_kernel = Philox + kick + phase + move, no control flow",
-                         "fp64_red_scattered_gops": atomic_peak},
+                         "atomic": {"achieved_gops": red_gops, "peak_gops": atomic_peak,
+                                    "frac": red_gops / atomic_peak if atomic_peak else None,
+                                    "reds_per_step": float(tm["local_reds"]) / max(float(tm["local_steps"]), 1.0),
+                                    "source": "red.global operations into the tallies counted by the kernel (rank 0) over its "
+                                              "kernel time; peak = scattered FP64 red microbenchmark over a PSD-sized array, live"}},
         }
+        if verify is not None:
+            out["verify"] = verify
         if world == 1 and not a.no_cpu_baseline:
-            v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads)
+            v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads, a.pcuts, all_species)
             out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
                                    "sample": f"{a.cpu_sample} particles per pcut, full pcut ladder, {st} steps, {s_it:.1f} s"}
             # the reference loop itself is serial (the threading directive at main_loops.jl:227 is a comment): one thread too
             n1 = max(a.cpu_sample // 10, 200)
-            v1, s1, st1 = cpu_arm(a.workload, n1, 1, 0, 1)
+            v1, s1, st1 = cpu_arm(a.workload, n1, 1, 0, 1, a.pcuts, all_species)
             out["cpu_baseline"]["single_thread"] = {"value": v1, "cores": 1,
                                                     "sample": f"{n1} particles per pcut, {st1} steps, {s1:.1f} s"}
         emit(out)

@@ -115,6 +115,10 @@ typedef struct McsConfig {
                             unbounded crossing log is not needed: 0 = off, 1 = on */
     int32_t dynamic_queue; /* 0 = particles dealt to warps in a fixed interleaved order (run-to-run deterministic tallies);
                               1 = global atomic work queue (load-balanced, summation order varies) */
+    int32_t det_tallies;   /* 1 (default) = the phase-space histogram, escape PSDs, coupled spectra, x_spec spectra and the
+                              energy pool are accumulated as exact fixed-point sums (integer atomics on 8 x 32-bit digits per
+                              cell): bitwise identical run to run, for any schedule and any number of GPUs;
+                              0 = red.global.add.f64 (summation order varies in the last bits).  CUDA library only. */
 } McsConfig;
 
 /* Per-species scalars read inside the loop (main_loops.jl:97-100, utils.jl:72-96). */
@@ -194,6 +198,7 @@ typedef struct McsTiming {
     double ion_loop_ms;  /* device time of whole mcs_run_ion calls (transport + split + counts + comm) */
     int64_t transport_launches, other_launches;
     int64_t local_steps, local_particles; /* this rank's scattering steps / particles entered into pcuts (before any all-reduce) */
+    int64_t local_reds;  /* red.global operations this rank issued into the tallies (FP64 cells + crossing counts) */
 } McsTiming;
 
 typedef struct McsHandle McsHandle;

@@ -51,6 +51,7 @@ class McsConfig(C.Structure):
         ("dont_scatter", _i32), ("use_custom_frg", _i32), ("use_custom_epsB", _i32),
         ("helix_cap", _i32), ("retro_cap", _i64), ("seed", _u64), ("compat", _u32),
         ("rng_mode", _i32), ("threads", _i32), ("bin_thermal", _i32), ("dynamic_queue", _i32),
+        ("det_tallies", _i32),
     ]
 
 
@@ -102,6 +103,7 @@ class McsTiming(C.Structure):
     _fields_ = [
         ("transport_ms", _d), ("split_ms", _d), ("reduce_ms", _d), ("h2d_ms", _d), ("d2h_ms", _d), ("comm_ms", _d), ("ion_loop_ms", _d),
         ("transport_launches", _i64), ("other_launches", _i64), ("local_steps", _i64), ("local_particles", _i64),
+        ("local_reds", _i64),
     ]
 
 

@@ -51,7 +51,7 @@ extern "C" void mcs_default_config(McsConfig* c) {
     for (int i = 0; i < MCS_MAX_IONS; i++) c->inj_fracs[i] = 1.0;
     c->do_retro = 1;
     c->helix_cap = 10000; c->retro_cap = 10000000; c->seed = 210; c->compat = MCS_COMPAT_DEFAULT;
-    c->rng_mode = MCS_RNG_PHILOX; c->threads = 1;
+    c->rng_mode = MCS_RNG_PHILOX; c->threads = 1; c->det_tallies = 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -102,6 +102,7 @@ struct McsHandle {
     int ng = 0, M = 0, T = 0;
     long long n_use = 0, first_global = 0, n_saved_last = 0, n_saved_global_last = 0;
     // device buffers
+    double2* d_az = nullptr;   // azimuth table of the fast loop: {sin, cos} of the 256 bin centres of phi_s
     double* d_boost = nullptr; // 3 arrays of (ng+2): ux/ut, uz/ut, ux*uz/ut^2
     double* d_grid = nullptr;  // 10 arrays of (ng+2): xg ux uz ut gsf gef bt sinth costh (bef unused) + tcuts(NA_C)
     double* d_zone = nullptr;  // eps_target, recv_pool [ng] each
@@ -135,12 +136,17 @@ struct McsHandle {
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
-    long long* d_gather = nullptr;
+    long long* d_gather = nullptr;    // [64 ranks][4]: {n_saved, n_use, error flag, spare} of the current pcut
     unsigned char* d_xchg = nullptr;  // all-gather buffer of saved records for the rebalancing split
     size_t xchg_bytes = 0;
+    bool reduced = false;             // mcs_end_ion already summed the tallies over ranks (idempotence)
+    bool split_timed = false;         // ev2/ev3 bracket an un-timed split (elapsed time read at the next sync)
+    unsigned long long steps0 = 0, saved0 = 0, reds0 = 0;  // counter values before the pcut in flight
     McsTiming tm;
     DevParams P;
 };
+
+static int check_index_range(long long first_global, long long n);
 
 static int pop_alloc(PopPtrs& p, long long n) {
     size_t nd = (size_t)n;
@@ -163,7 +169,7 @@ extern "C" int mcs_destroy(McsHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    cudaFree(h->d_grid); cudaFree(h->d_boost); cudaFree(h->d_zone);
+    cudaFree(h->d_grid); cudaFree(h->d_boost); cudaFree(h->d_zone); cudaFree(h->d_az);
     for (auto& p : h->pop) pop_free(p);
     cudaFree(h->d_l_save); cudaFree(h->d_fate); cudaFree(h->d_helix); cudaFree(h->d_retro); cudaFree(h->d_draws);
     cudaFree(h->d_saved_idx); cudaFree(h->d_block_off); cudaFree(h->d_total); cudaFree(h->d_block_cnt);
@@ -228,6 +234,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     CUA(cudaMalloc(&h->d_grid, (size_t)(9 * ng2 + MCS_NA_C) * 8));
     CUA(cudaMalloc(&h->d_boost, (size_t)3 * ng2 * 8));
     CUA(cudaMalloc(&h->d_zone, (size_t)2 * ng * 8));
+    CUA(cudaMalloc(&h->d_az, (size_t)AZ_N * sizeof(double2)));
     for (auto& p : h->pop) TRY(pop_alloc(p, N));
     CUA(cudaMalloc(&h->d_l_save, (size_t)N)); CUA(cudaMalloc(&h->d_fate, (size_t)N * 4)); CUA(cudaMalloc(&h->d_helix, (size_t)N * 4));
     CUA(cudaMalloc(&h->d_retro, (size_t)N * 8)); CUA(cudaMalloc(&h->d_draws, (size_t)N * 8));
@@ -248,18 +255,13 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     CUA(cudaMalloc(&h->d_u64, (size_t)(ng + CNT_N) * 8));
     const size_t L = (size_t)(cfg->na_cr > 0 ? cfg->na_cr : 1);
     CUA(cudaMalloc(&h->d_tg, L * 8)); CUA(cudaMalloc(&h->d_tpx, L * 8)); CUA(cudaMalloc(&h->d_tpt, L * 8)); CUA(cudaMalloc(&h->d_tw, L * 8));
-    CUA(cudaMalloc(&h->d_partials, (size_t)h->max_blocks * (4 * ng + SC_N) * 8));
-    CUA(cudaMalloc(&h->d_gather, 64 * 8));
+    CUA(cudaMalloc(&h->d_partials, (size_t)h->max_blocks * (3 * ng + SC_N) * 8));
+    CUA(cudaMalloc(&h->d_gather, 64 * 4 * 8));
     CUA(cudaMemsetAsync(h->d_tally, 0, o * 8, h->stream));
     CUA(cudaMemsetAsync(h->d_u64, 0, (size_t)(ng + CNT_N) * 8, h->stream));
-    while (h->block > 32 && (size_t)(h->block / 32) * warp_smem_bytes(ng) > (size_t)100 * 1024) h->block /= 2;
-    {
-        const int smem = (int)((size_t)(h->block / 32) * warp_smem_bytes(ng));
-        CUA(cudaFuncSetAttribute(transport_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUA(cudaFuncSetAttribute(transport_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUA(cudaFuncSetAttribute(transport_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUA(cudaFuncSetAttribute(transport_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
+    // large grids: fewer warps per block so that the per-warp flux partials still fit (the per-launch shared-memory
+    // attribute is set in mcs_run_pcut: it belongs to the function and the device, not to this handle)
+    while (h->block > 32 && block_smem_bytes(ng, h->block / 32) > (size_t)200 * 1024 / (size_t)h->blocks_per_sm) h->block /= 2;
 #undef TRY
 #undef CUA
     // static part of the kernel parameters
@@ -287,6 +289,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
             P.omc[k] = 1 - cos(sqrt(6 * (TWO_PI * 1.0) / (xn[k] * (cfg->eta_mfp * 1.0))));
             P.inv_xn[k] = 1.0 / xn[k];
             P.dphi[k] = TWO_PI / xn[k];
+            P.cdphi[k] = cos(P.dphi[k]); P.sdphi[k] = sin(P.dphi[k]);
         }
     }
     P.key0 = (uint32_t)cfg->seed; P.key1 = (uint32_t)(cfg->seed >> 32);
@@ -296,6 +299,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     P.bt = g + 6 * ng2; P.sinth = g + 7 * ng2; P.costh = g + 8 * ng2; P.tcuts = g + 9 * ng2;
     P.rxt = h->d_boost; P.rzt = h->d_boost + ng2; P.crt = h->d_boost + 2 * ng2;
     P.eps_target = h->d_zone; P.recv_pool = h->d_zone + ng;
+    P.az_tab = h->d_az;
     P.l_save = h->d_l_save; P.fate = h->d_fate; P.helix = h->d_helix; P.retro = h->d_retro; P.draws = h->d_draws;
     TallyPtrs& t = P.t;
     double* b = h->d_tally;
@@ -305,8 +309,19 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     t.therm_sf = cfg->bin_thermal ? b + h->off_thsf : nullptr; t.therm_pf = cfg->bin_thermal ? b + h->off_thpf : nullptr;
     t.dndp_cr = cfg->bin_thermal ? b + h->off_dndp : nullptr;
     t.counters = h->d_u64 + ng;
+    t.ncross = h->d_u64;
     t.tg = h->d_tg; t.tpx = h->d_tpx; t.tpt = h->d_tpt; t.tw = h->d_tw; t.na_cr = cfg->na_cr;
     t.block_partials = h->d_partials;
+    {
+        double2 az[AZ_N];  // host libm: sine and cosine of the bin centres of the scattering azimuth
+        for (int k = 0; k < AZ_N; k++) {
+            const double a = -PI + TWO_PI * (k + 0.5) / AZ_N;
+            az[k].x = sin(a); az[k].y = cos(a);
+        }
+        cudaError_t e2 = cudaMemcpyAsync(h->d_az, az, sizeof az, cudaMemcpyHostToDevice, h->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(h->stream);
+        if (e2 != cudaSuccess) { mcs_destroy(h); return fail(MCS_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e2)); }
+    }
     {
         cudaError_t e2 = cudaMemcpyAsync((void*)P.tcuts, cfg->tcuts, MCS_NA_C * 8, cudaMemcpyHostToDevice, h->stream);
         if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(h->stream);
@@ -335,6 +350,14 @@ extern "C" int mcs_comm_init(McsHandle* h, int rank, int nranks, const void* id1
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
     NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    // Exchange buffer of the rebalancing split, sized for the worst case (every rank saves its whole population) here,
+    // where a failure is reported to each caller before any collective: inside the pcut loop a rank that bailed out
+    // alone would leave the others blocked in the next all-gather.
+    const size_t stride_max = ((size_t)h->cfg.n_pts_max + 15) / 16 * 16;
+    const size_t need = stride_max * 82 * (size_t)nranks;
+    cudaFree(h->d_xchg); h->d_xchg = nullptr; h->xchg_bytes = 0;
+    if (cudaMalloc(&h->d_xchg, need) != cudaSuccess) return fail(MCS_ERR_NOMEM, "cannot allocate the split exchange buffer");
+    h->xchg_bytes = need;
     return MCS_OK;
 }
 
@@ -349,9 +372,11 @@ extern "C" int mcs_set_profile(McsHandle* h, int32_t n_grid, const double* xg, c
     std::vector<double> buf((size_t)9 * ng2 + 2 * h->ng, 0.0);
     const double* src[7] = {xg, ux, uz, ut, gsf, gef, bt};
     for (int a = 0; a < 7; a++) memcpy(&buf[(size_t)a * ng2], src[a], (size_t)ng2 * 8);
+    h->P.oblique = 0;
     for (int i = 0; i < ng2; i++) {  // per-zone sin/cos(theta_B) tables (particle_loop.jl:203-204), host libm
         buf[(size_t)7 * ng2 + i] = sin(th[i]);
         buf[(size_t)8 * ng2 + i] = cos(th[i]);
+        if (buf[(size_t)7 * ng2 + i] != 0.0) h->P.oblique = 1;
     }
     if (eps_target) memcpy(&buf[(size_t)9 * ng2], eps_target, (size_t)h->ng * 8);
     if (recv_pool) memcpy(&buf[(size_t)9 * ng2 + h->ng], recv_pool, (size_t)h->ng * 8);
@@ -379,8 +404,9 @@ extern "C" int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const 
         return fail(MCS_ERR_ARG, "weight/ptot_pf/pb_pf/x_cm/grid/phi_rad are required");
     for (int64_t i = 0; i < n; i++)
         if (pop->grid[i] < 0 || pop->grid[i] > h->ng + 1) return fail(MCS_ERR_ARG, "grid index out of range");
+    { int rcg = check_index_range(first_global, n); if (rcg) return rcg; }
     CU(cudaSetDevice(h->device));
-    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion;
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->split_timed = false;
     h->n_use = n; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     // clear_psd! (ion_init.jl:1-16) and every other per-ion sum
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
@@ -422,8 +448,10 @@ extern "C" int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_io
     if (n_local < 0 || first_global < 0 || first_global + n_local > n_total) return fail(MCS_ERR_ARG, "shard outside the population");
     if (n_local > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "n_pts exceeds n_pts_max");
     if (inj->grid < 0 || inj->grid > h->ng + 1) return fail(MCS_ERR_ARG, "grid index out of range");
+    { int rcg = check_index_range(first_global, n_local); if (rcg) return rcg; }
+    if (n_total > 0x100000000ll) return fail(MCS_ERR_ARG, "global particle index exceeds 2^32 (RNG counter width)");
     CU(cudaSetDevice(h->device));
-    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion;
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->split_timed = false;
     h->n_use = n_local; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
     CU(cudaMemsetAsync(h->d_u64, 0, (size_t)(h->ng + CNT_N) * 8, h->stream));
@@ -465,12 +493,21 @@ static int read_counters(McsHandle* h) {
     return MCS_OK;
 }
 
-extern "C" int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_prev, int64_t* n_saved, int64_t* n_steps) {
-    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
-    CU(cudaSetDevice(h->device));
+// RNG counters hold the GLOBAL particle index in 32 bits and the pcut in 16: refuse anything that would wrap and
+// silently reuse a stream.
+static int check_index_range(long long first_global, long long n) {
+    if (n > 0x7fffffffll) return fail(MCS_ERR_ARG, "more than 2^31-1 particles on one rank");
+    if (first_global < 0 || first_global + n > 0x100000000ll) return fail(MCS_ERR_ARG, "global particle index exceeds 2^32 (RNG counter width)");
+    return MCS_OK;
+}
+
+// Launch the transport kernel of one pcut and the ordered reduction of its block partials; no host synchronisation.
+static int launch_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_prev) {
+    if (i_pcut < 0 || i_pcut > 0xFFFF) return fail(MCS_ERR_ARG, "i_pcut outside the RNG counter's 16-bit field");
     const long long n = h->n_use;
-    const unsigned long long steps0 = h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO];
-    const unsigned long long saved0 = h->h_counters[CNT_FATE0];
+    h->steps0 = h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO];
+    h->saved0 = h->h_counters[CNT_FATE0];
+    h->reds0 = h->h_counters[CNT_RED];
     DevParams& P = h->P;
     P.aa = h->sp.aa; P.zz = h->sp.zz_esu; P.n0 = h->sp.n0; P.pmax_cutoff = h->sp.pmax_cutoff; P.ewf = h->sp.electron_weight_fac;
     P.m = P.aa * P.mp; P.mc = P.m * P.c; P.inj_frac = h->cfg.inj_fracs[h->i_ion - 1];
@@ -497,67 +534,60 @@ extern "C" int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pc
     // l_save .= false (main_loops.jl:184); the *_saved arrays are only read where l_save is set
     CU(cudaMemsetAsync(h->d_l_save, 0, (size_t)(n > 0 ? n : 1), h->stream));
     CU(cudaMemsetAsync(h->d_u64 + h->ng + CNT_QUEUE, 0, 8, h->stream));
+    CU(cudaEventRecord(h->ev0, h->stream));
     if (n > 0) {
         long long want = (n + h->block - 1) / h->block;
         int blocks = (int)(want < h->max_blocks ? want : h->max_blocks);
-        size_t smem = (size_t)(h->block / 32) * warp_smem_bytes(h->ng);
+        const size_t smem = block_smem_bytes(h->ng, h->block / 32);
         const bool electron = h->sp.aa < 1;
-        CU(cudaEventRecord(h->ev0, h->stream));
-        if (debug) {
-            if (electron) transport_kernel<true, true><<<blocks, h->block, smem, h->stream>>>(P);
-            else transport_kernel<true, false><<<blocks, h->block, smem, h->stream>>>(P);
-        } else {
-            if (electron) transport_kernel<false, true><<<blocks, h->block, smem, h->stream>>>(P);
-            else transport_kernel<false, false><<<blocks, h->block, smem, h->stream>>>(P);
-        }
+        void (*kern)(const DevParams) = debug ? (electron ? transport_kernel<true, true> : transport_kernel<true, false>)
+                                              : (electron ? transport_kernel<false, true> : transport_kernel<false, false>);
+        // per function and per device, not per handle: set for THIS launch (another handle may have a smaller grid)
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<blocks, h->block, smem, h->stream>>>(P);
         CU(cudaEventRecord(h->ev1, h->stream));
         CU(cudaGetLastError());
         double* b = h->d_tally;
-        reduce_partials_kernel<<<(4 * h->ng + SC_N + 127) / 128, 128, 0, h->stream>>>(
-            h->d_partials, blocks, h->ng, b + h->off_pxx, b + h->off_pxz, b + h->off_efl, h->d_u64, b + h->off_scal);
+        reduce_partials_kernel<<<(3 * h->ng + SC_N + 127) / 128, 128, 0, h->stream>>>(
+            h->d_partials, blocks, h->ng, b + h->off_pxx, b + h->off_pxz, b + h->off_efl, b + h->off_scal);
         CU(cudaGetLastError());
         h->tm.transport_launches++; h->tm.other_launches++;
+    } else {
+        CU(cudaEventRecord(h->ev1, h->stream));
     }
-    int rc = read_counters(h);
-    if (rc) return rc;
-    if (n > 0) {
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        h->tm.transport_ms += ms;
-    }
-    h->n_saved_last = (long long)(h->h_counters[CNT_FATE0] - saved0);
-    h->tm.local_steps += (int64_t)(h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO] - steps0);
-    h->tm.local_particles += n;
-    if (n_saved) *n_saved = h->n_saved_last;
-    if (n_steps) *n_steps = (int64_t)(h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO] - steps0);
     return MCS_OK;
 }
 
-static int compact_saved(McsHandle* h);
-
-extern "C" int mcs_split_explicit(McsHandle* h, int64_t i_mult, int64_t first_global_child, int64_t* n_new_local) {
-    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
-    if (i_mult < 1) return fail(MCS_ERR_ARG, "i_mult < 1");
-    const long long n = h->n_use, ns = h->n_saved_last, n_out = ns * i_mult;
-    if (n_out > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "split population exceeds n_pts_max");
-    CU(cudaSetDevice(h->device));
-    CU(cudaEventRecord(h->ev2, h->stream));
-    if (ns > 0) {
-        int rc = compact_saved(h);
-        if (rc) return rc;
-        clone_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, h->stream>>>(h->pop[1], h->pop[h->nxt], h->d_saved_idx, n_out, i_mult);
-        CU(cudaGetLastError());
-        h->tm.other_launches++;
-    }
-    CU(cudaEventRecord(h->ev3, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+// After a synchronisation that brought h_counters back: book-keeping of the pcut just run.
+static int finish_pcut(McsHandle* h, int64_t* n_saved, int64_t* n_steps) {
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
-    h->tm.split_ms += ms;
-    int t = h->cur; h->cur = h->nxt; h->nxt = t;
-    h->n_use = n_out; h->first_global = first_global_child;
-    if (n_new_local) *n_new_local = n_out;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->tm.transport_ms += ms;
+    if (h->split_timed) {
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        h->tm.split_ms += ms;
+        h->split_timed = false;
+    }
+    const int64_t st = (int64_t)(h->h_counters[CNT_HELIX] + h->h_counters[CNT_RETRO] - h->steps0);
+    h->n_saved_last = (long long)(h->h_counters[CNT_FATE0] - h->saved0);
+    h->tm.local_steps += st;
+    h->tm.local_particles += h->n_use;
+    h->tm.local_reds += (int64_t)(h->h_counters[CNT_RED] - h->reds0);
+    if (n_saved) *n_saved = h->n_saved_last;
+    if (n_steps) *n_steps = st;
     return MCS_OK;
+}
+
+extern "C" int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_prev, int64_t* n_saved, int64_t* n_steps) {
+    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    if (h->reduced) return fail(MCS_ERR_STATE, "mcs_end_ion already summed this ion's tallies: mcs_begin_ion first");
+    CU(cudaSetDevice(h->device));
+    int rc = launch_pcut(h, i_pcut, pcut, pcut_prev);
+    if (rc) return rc;
+    rc = read_counters(h);
+    if (rc) return rc;
+    return finish_pcut(h, n_saved, n_steps);
 }
 
 // Local part of new_pcut: order-preserving list of the saved indices (h->d_saved_idx[0..ns))
@@ -574,50 +604,71 @@ static int compact_saved(McsHandle* h) {
     return MCS_OK;
 }
 
-extern "C" int mcs_split(McsHandle* h, int64_t n_pts_target, int64_t* n_new_local, int64_t* n_new_global, int64_t* i_mult_out) {
-    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
-    if (h->nranks == 1) {
-        const long long ns = h->n_saved_last;
-        h->n_saved_global_last = ns;
-        if (ns <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
-        long long i_mult = n_pts_target / ns;  // cuts.jl:42
-        if (i_mult < 1) i_mult = 1;
-        int64_t k = 0;
-        int rc = mcs_split_explicit(h, i_mult, 0, &k);
-        if (rc) return rc;
-        if (n_new_local) *n_new_local = k;
-        if (n_new_global) *n_new_global = k;
-        if (i_mult_out) *i_mult_out = i_mult;
-        return MCS_OK;
-    }
-    // ---- multi-GPU: all-gather the saved records, every rank clones an equal slice of the global child range ----
-    CU(cudaSetDevice(h->device));
+// Single-rank split, enqueued only (the caller synchronises).  ev2/ev3 bracket it.
+static int split_local_async(McsHandle* h, int64_t i_mult, int64_t first_global_child, int64_t* n_new_local) {
+    if (i_mult < 1) return fail(MCS_ERR_ARG, "i_mult < 1");
+    const long long ns = h->n_saved_last, n_out = ns * i_mult;
+    if (n_out > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "split population exceeds n_pts_max");
+    int rc = check_index_range(first_global_child, n_out);
+    if (rc) return rc;
     CU(cudaEventRecord(h->ev2, h->stream));
-    long long v = h->n_saved_last, all[64];
-    CU(cudaMemcpyAsync(h->d_gather + h->rank, &v, 8, cudaMemcpyHostToDevice, h->stream));
-    NC(g_nccl.AllGather(h->d_gather + h->rank, h->d_gather, 1, ncclInt64, h->comm, h->stream));
-    CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (ns > 0) {
+        rc = compact_saved(h);
+        if (rc) return rc;
+        clone_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, h->stream>>>(h->pop[1], h->pop[h->nxt], h->d_saved_idx, n_out, i_mult);
+        CU(cudaGetLastError());
+        h->tm.other_launches++;
+    }
+    CU(cudaEventRecord(h->ev3, h->stream));
+    h->split_timed = true;
+    int t = h->cur; h->cur = h->nxt; h->nxt = t;
+    h->n_use = n_out; h->first_global = first_global_child;
+    if (n_new_local) *n_new_local = n_out;
+    return MCS_OK;
+}
+
+static int sync_split_time(McsHandle* h) {
     CU(cudaStreamSynchronize(h->stream));
+    if (h->split_timed) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
+        h->tm.split_ms += ms;
+        h->split_timed = false;
+    }
+    return MCS_OK;
+}
+
+extern "C" int mcs_split_explicit(McsHandle* h, int64_t i_mult, int64_t first_global_child, int64_t* n_new_local) {
+    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    CU(cudaSetDevice(h->device));
+    int rc = split_local_async(h, i_mult, first_global_child, n_new_local);
+    if (rc) return rc;
+    return sync_split_time(h);
+}
+
+// Multi-GPU split with rebalancing, enqueued only: all-gather the saved records, every rank clones an equal slice of the
+// GLOBAL child range.  `ns_all` = saved particles per rank (identical on every rank), so every decision below — i_mult,
+// the slices, the capacity check — comes out the same everywhere and no rank can leave the collective alone.
+static int split_multi_async(McsHandle* h, const long long* ns_all, int64_t n_pts_target, int64_t* n_new_local,
+                             int64_t* n_new_global, int64_t* i_mult_out) {
     GatherPrefix pre;
     memset(&pre, 0, sizeof pre);
     pre.nranks = h->nranks;
     long long S = 0, max_ns = 0;
-    for (int r = 0; r < h->nranks; r++) { pre.start[r] = S; S += all[r]; if (all[r] > max_ns) max_ns = all[r]; }
+    for (int r = 0; r < h->nranks; r++) { pre.start[r] = S; S += ns_all[r]; if (ns_all[r] > max_ns) max_ns = ns_all[r]; }
     pre.start[h->nranks] = S;
     h->n_saved_global_last = S;
     if (S <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
     long long i_mult = n_pts_target / S;  // cuts.jl:42 on the GLOBAL count
     if (i_mult < 1) i_mult = 1;
     const long long C = S * i_mult;
+    for (int r = 0; r < h->nranks; r++)  // the largest slice decides for everybody
+        if (C * (r + 1) / h->nranks - C * r / h->nranks > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "split population exceeds n_pts_max");
+    if (C > 0x100000000ll) return fail(MCS_ERR_ARG, "global particle index exceeds 2^32 (RNG counter width)");
     const long long c0 = C * h->rank / h->nranks, c1 = C * (h->rank + 1) / h->nranks, n_out = c1 - c0;
-    if (n_out > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "split population exceeds n_pts_max");
     const long long stride = (max_ns + 15) / 16 * 16;
-    const size_t need = (size_t)stride * 82 * (size_t)h->nranks;
-    if (need > h->xchg_bytes) {
-        cudaFree(h->d_xchg); h->d_xchg = nullptr; h->xchg_bytes = 0;
-        CU(cudaMalloc(&h->d_xchg, need + need / 4));
-        h->xchg_bytes = need + need / 4;
-    }
+    if ((size_t)stride * 82 * (size_t)h->nranks > h->xchg_bytes) return fail(MCS_ERR_STATE, "split exchange buffer too small");
+    CU(cudaEventRecord(h->ev2, h->stream));
     int rc = compact_saved(h);
     if (rc) return rc;
     unsigned char* mine = h->d_xchg + (size_t)h->rank * (size_t)stride * 82;
@@ -635,10 +686,7 @@ extern "C" int mcs_split(McsHandle* h, int64_t n_pts_target, int64_t* n_new_loca
         h->tm.other_launches++;
     }
     CU(cudaEventRecord(h->ev3, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, h->ev2, h->ev3));
-    h->tm.split_ms += ms;
+    h->split_timed = true;
     int t = h->cur; h->cur = h->nxt; h->nxt = t;
     h->n_use = n_out; h->first_global = c0;
     if (n_new_local) *n_new_local = n_out;
@@ -647,58 +695,108 @@ extern "C" int mcs_split(McsHandle* h, int64_t n_pts_target, int64_t* n_new_loca
     return MCS_OK;
 }
 
-static int global_sum_ll(McsHandle* h, long long v, long long* out) {
-    if (h->nranks == 1) { *out = v; return MCS_OK; }
-    long long all[64];
-    CU(cudaMemcpyAsync(h->d_gather + h->rank, &v, 8, cudaMemcpyHostToDevice, h->stream));
-    NC(g_nccl.AllGather(h->d_gather + h->rank, h->d_gather, 1, ncclInt64, h->comm, h->stream));
-    CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 8, cudaMemcpyDeviceToHost, h->stream));
+// ONE exchange per pcut: every rank contributes {n_saved, n_use, error flag}; all ranks get all triples.
+// n_saved is computed on the device from the counter (so no host round trip is needed before the gather) when
+// `from_device` is set, else taken from h->n_saved_last.
+static int gather_counts(McsHandle* h, bool from_device, long long local_err, long long* ns_all, long long* used_g, long long* err_any) {
+    long long all[64 * 4];
+    if (from_device) {
+        pack_counts_kernel<<<1, 1, 0, h->stream>>>(h->d_u64 + h->ng, h->saved0, h->n_use, local_err, h->d_gather + 4 * h->rank);
+        CU(cudaGetLastError());
+        h->tm.other_launches++;
+    } else {
+        long long v[4] = {h->n_saved_last, h->n_use, local_err, 0};
+        CU(cudaMemcpyAsync(h->d_gather + 4 * h->rank, v, 32, cudaMemcpyHostToDevice, h->stream));
+    }
+    NC(g_nccl.AllGather(h->d_gather + 4 * h->rank, h->d_gather, 4, ncclInt64, h->comm, h->stream));
+    CU(cudaMemcpyAsync(all, h->d_gather, (size_t)h->nranks * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_counters, h->d_u64 + h->ng, CNT_N * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    long long s = 0;
-    for (int r = 0; r < h->nranks; r++) s += all[r];
-    *out = s;
+    long long u = 0, e = 0;
+    for (int r = 0; r < h->nranks; r++) { ns_all[r] = all[4 * r]; u += all[4 * r + 1]; e |= all[4 * r + 2]; }
+    *used_g = u; *err_any = e;
     return MCS_OK;
 }
 
+extern "C" int mcs_split(McsHandle* h, int64_t n_pts_target, int64_t* n_new_local, int64_t* n_new_global, int64_t* i_mult_out) {
+    if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    CU(cudaSetDevice(h->device));
+    if (h->nranks == 1) {
+        const long long ns = h->n_saved_last;
+        h->n_saved_global_last = ns;
+        if (ns <= 0) return fail(MCS_ERR_STATE, "no saved particles to split");
+        long long i_mult = n_pts_target / ns;  // cuts.jl:42
+        if (i_mult < 1) i_mult = 1;
+        int64_t k = 0;
+        int rc = split_local_async(h, i_mult, 0, &k);
+        if (rc) return rc;
+        if (n_new_local) *n_new_local = k;
+        if (n_new_global) *n_new_global = k;
+        if (i_mult_out) *i_mult_out = i_mult;
+        return sync_split_time(h);
+    }
+    long long ns_all[64], used_g = 0, err_any = 0;
+    int rc = gather_counts(h, false, 0, ns_all, &used_g, &err_any);
+    if (rc) return rc;
+    rc = split_multi_async(h, ns_all, n_pts_target, n_new_local, n_new_global, i_mult_out);
+    if (rc) return rc;
+    return sync_split_time(h);
+}
+
+// Whole pcut loop of one ion (main_loops.jl:179-317).  Host synchronisations: ONE per pcut (the counts), none for the split.
 extern "C" int mcs_run_ion(McsHandle* h, const double* pcuts, int32_t n_pcuts, double p_pcut_hi, int64_t n_pts_pcut,
                            int64_t n_pts_pcut_hi, int32_t* n_run, int64_t* n_used, int64_t* n_saved_arr) {
     if (!h || !pcuts || n_pcuts < 1 || n_pcuts > MCS_NA_C) return fail(MCS_ERR_ARG, "bad pcuts");
+    if (!h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    if (h->reduced) return fail(MCS_ERR_STATE, "mcs_end_ion already summed this ion's tallies: mcs_begin_ion first");
     int32_t k = 0;
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev4, h->stream));
+    int rc_out = MCS_OK;
     for (int32_t i = 1; i <= n_pcuts; i++) {
-        int64_t ns = 0, nst = 0;
-        long long used_g = 0;
-        int rc = global_sum_ll(h, h->n_use, &used_g);
-        if (rc) return rc;
-        if (n_used) n_used[i - 1] = used_g;
-        rc = mcs_run_pcut(h, i, pcuts[i - 1], i > 1 ? pcuts[i - 2] : 0.0, &ns, &nst);
-        if (rc) return rc;
-        k = i;
-        int64_t target = pcuts[i - 1] < p_pcut_hi ? n_pts_pcut : n_pts_pcut_hi;
+        int64_t ns = 0;
+        long long used_g = h->n_use, ns_g = 0, ns_all[64], err_any = 0;
+        // A failure that only this rank sees must not make it leave before the exchange: it is carried as a flag
+        // through the gather so that every rank returns together.
+        int rc = launch_pcut(h, i, pcuts[i - 1], i > 1 ? pcuts[i - 2] : 0.0);
         if (h->nranks == 1) {
-            if (n_saved_arr) n_saved_arr[i - 1] = ns;
-            if (ns == 0) break;  // pcut_finalize: break_pcut
-            rc = mcs_split(h, target, nullptr, nullptr, nullptr);
             if (rc) return rc;
+            rc = read_counters(h);
+            if (rc) return rc;
+            rc = finish_pcut(h, &ns, nullptr);
+            if (rc) return rc;
+            ns_g = ns;
         } else {
-            // every rank must take the same branch: decide on the global count
-            long long ns_g = 0;
-            rc = global_sum_ll(h, ns, &ns_g);
+            int rc2 = gather_counts(h, true, rc != MCS_OK, ns_all, &used_g, &err_any);
+            if (rc2) return rc2;
+            if (err_any) { rc_out = rc ? rc : fail(MCS_ERR_COMM, "another rank failed in this pcut"); break; }
+            rc = finish_pcut(h, &ns, nullptr);
             if (rc) return rc;
-            if (n_saved_arr) n_saved_arr[i - 1] = ns_g;
-            if (ns_g == 0) break;
-            rc = mcs_split(h, target, nullptr, nullptr, nullptr);
-            if (rc) return rc;
+            for (int r = 0; r < h->nranks; r++) ns_g += ns_all[r];
         }
+        if (n_used) n_used[i - 1] = used_g;
+        if (n_saved_arr) n_saved_arr[i - 1] = ns_g;
+        k = i;
+        if (ns_g == 0) break;  // pcut_finalize: break_pcut (decided on the global count: every rank takes the same branch)
+        const int64_t target = pcuts[i - 1] < p_pcut_hi ? n_pts_pcut : n_pts_pcut_hi;
+        if (h->nranks == 1) {
+            long long i_mult = target / ns_g;  // cuts.jl:42
+            if (i_mult < 1) i_mult = 1;
+            h->n_saved_global_last = ns_g;
+            rc = split_local_async(h, i_mult, 0, nullptr);
+        } else {
+            rc = split_multi_async(h, ns_all, target, nullptr, nullptr, nullptr);  // errors here are decided identically on every rank
+        }
+        if (rc) { rc_out = rc; break; }
     }
     CU(cudaEventRecord(h->ev5, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    int rc = sync_split_time(h);
+    if (rc) return rc;
     float ms_loop = 0;
     CU(cudaEventElapsedTime(&ms_loop, h->ev4, h->ev5));
     h->tm.ion_loop_ms += ms_loop;
     if (n_run) *n_run = k;
-    return MCS_OK;
+    return rc_out;
 }
 
 extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
@@ -710,7 +808,8 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     if (rc) return rc;
     const long long log_claimed = (long long)h->h_counters[CNT_LOG];
     const long long n_log = log_claimed < h->cfg.na_cr ? log_claimed : h->cfg.na_cr;
-    if (h->nranks > 1) {  // ONE all-reduce over the packed FP64 tallies (+ one for the integer counts)
+    if (h->nranks > 1 && !h->reduced) {  // ONE all-reduce over the packed FP64 tallies (+ one for the integer counts)
+        h->reduced = true;  // a second call returns the same sums; further pcuts need mcs_begin_ion
         CU(cudaEventRecord(h->ev2, h->stream));
         NC(g_nccl.AllReduce(h->d_tally, h->d_tally, h->n_tally, ncclFloat64, ncclSum, h->comm, h->stream));
         NC(g_nccl.AllReduce(h->d_u64, h->d_u64, (size_t)(h->ng + CNT_N), ncclUint64, ncclSum, h->comm, h->stream));

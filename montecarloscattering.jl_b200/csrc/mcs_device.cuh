@@ -30,7 +30,7 @@
 #define MCS_BLOCK 256
 #endif
 #ifndef MCS_MIN_BLOCKS
-#define MCS_MIN_BLOCKS 2
+#define MCS_MIN_BLOCKS 3
 #endif
 #ifndef MCS_PARK_T
 #define MCS_PARK_T 16     // lanes that must be waiting (parked or refillable) before the warp leaves the fast loop
@@ -57,7 +57,11 @@ constexpr double HALF_PI = PI / 2;
 constexpr double SIN_UPPER_LIMIT = 0.99999999999999989;  // prevfloat(1.0), scattering.jl:3
 constexpr double SPIKE_AWAY = 1000.0;                    // all_flux.jl:4, particle_finish.jl:5
 constexpr int E1 = MCS_PSD_MAX + 1;
-constexpr int QCAP = 64;  // per-warp event queue: < 32 left after a drain + at most 1 event per lane per push point
+#ifndef MCS_QCAP
+#define MCS_QCAP 64
+#endif
+constexpr int QCAP = MCS_QCAP;  // per-warp event queue: < 32 left after a drain + up to 32 new events per push point; below 64
+                                // the queue is drained early when a push would not fit (push_events)
 constexpr unsigned FULL = 0xffffffffu;
 
 enum : uint32_t {
@@ -81,7 +85,9 @@ enum { SC_ESC_FLUX = 0, SC_PX_ESC_FEB, SC_EN_ESC_FEB, SC_SUMP, SC_SUMKE, SC_PX_E
 enum {
     CNT_HELIX = 0, CNT_RETRO, CNT_W_PPERP, CNT_W_PSDMOM, CNT_NEGSQRT, CNT_RETRO_CAP, CNT_ERR, CNT_FATE0,  // ..FATE5 = 12
     CNT_LOG = 13, CNT_LOG_OVER = 14, CNT_SAVED = 15, CNT_QUEUE = 16, CNT_FAST_LANE = 17, CNT_FAST_ITER = 18, CNT_SLOW_SEC = 19,
-    CNT_SLOW_LANE = 20, CNT_PARK0 = 24, CNT_N = 40  // CNT_PARK0..+15: why lanes left the fast loop (MCS_SCHED_STATS)
+    CNT_SLOW_LANE = 20,
+    CNT_RED = 21,  // red.global issued into the tallies (FP64 cells + crossing counts): the kernel's atomic work
+    CNT_PARK0 = 24, CNT_N = 40  // CNT_PARK0..+15: why lanes left the fast loop (MCS_SCHED_STATS)
 };
 
 struct TallyPtrs {
@@ -102,7 +108,8 @@ struct TallyPtrs {
     long long* tg;          // thermal-crossing log
     double *tpx, *tpt, *tw;
     long long na_cr;
-    double* block_partials; // [gridDim.x][4*n_grid + SC_N]: pxx | pxz | efl | crossings (u64 bits) | scalars
+    unsigned long long* ncross;  // [n_grid] thermal crossings per zone (integer adds: any order gives the same bits)
+    double* block_partials; // [gridDim.x][3*n_grid + SC_N]: pxx | pxz | efl | scalars
 };
 
 struct DevParams {
@@ -112,8 +119,11 @@ struct DevParams {
     double energy_transfer_frac, feb_up, feb_dn, x_grid_stop, B_CMBz, xn_fine, xn_coarse, age_max;
     // per-xn_per scattering constants, [0] fine [1] coarse: 1-cos_max (scattering.jl:46-60), 1/xn_per, 2pi/xn_per
     double omc[2], inv_xn[2], dphi[2];
+    double cdphi[2], sdphi[2];   // cos / sin of dphi (the fast loop advances the gyro-phase as a rotation)
+    const double2* az_tab;       // [AZ_N] {sin, cos} of -pi + 2 pi (k + 1/2) / AZ_N
     double x_spec[MCS_MAX_XSPEC];
     int M, T, n_grid, i_grid_feb, i_shock, n_xspec, n_tcuts, helix_cap;
+    int oblique;  // some zone has sin(theta_B) != 0 (the reference refuses those profiles; the move keeps the term)
     long long retro_cap;
     uint32_t flags;
     // species
@@ -142,29 +152,50 @@ struct DevParams {
     int trace_max;
 };
 
+// Shared memory of one block: [zone table | warp 0 region | warp 1 region | ...].
+//  zone table (fast loop): per grid node i = 0..ng+1 three 16-byte pairs {ux, gsf}, {gef, cos th}, {xg[i], xg[i+1]} and the gyro
+//  denominator 1/(zz*btot[i]); a pass reads its zone's constants from here instead of holding them in registers.
+//  warp region: flux partials pxx | pxz | efl (ng each) | scalars (SC_N), then the event queue (QCAP x 64 B, SoA).
+//  azimuth table (fast loop): 256 x {sin, cos} of the bin centres of the scattering azimuth (see az_sincos).
+constexpr int AZ_N = 256;
+__host__ __device__ inline size_t zone_tab_bytes(int ng) { return ((((size_t)(ng + 2) * 56) + 15) & ~(size_t)15) + (size_t)AZ_N * 16; }
 __host__ __device__ inline size_t warp_smem_bytes(int ng) {
-    return (size_t)(4 * ng + SC_N) * 8 + (size_t)QCAP * (6 * 8 + 4 * 4);
+    return (size_t)(3 * ng + SC_N) * 8 + (size_t)QCAP * (7 * 8 + 4 * 4);
 }
+__host__ __device__ inline size_t block_smem_bytes(int ng, int warps) { return zone_tab_bytes(ng) + (size_t)warps * warp_smem_bytes(ng); }
 
 // per-warp shared-memory view
 struct WarpMem {
-    double* part;  // [4*ng + SC_N]: pxx | pxz | efl | crossings(u64) | scalars
-    double *q_pb, *q_pperp, *q_gam, *q_phi, *q_w, *q_ptot;
+    double* part;  // [3*ng + SC_N]: pxx | pxz | efl | scalars
+    double *q_pb, *q_pperp, *q_gam, *q_cphi, *q_sphi, *q_w, *q_ptot;  // the gyro-phase travels as (cos, sin)
     int *q_inew, *q_iold, *q_iz;
     uint32_t* q_flags;
 };
 
-__device__ __forceinline__ WarpMem warp_mem(unsigned char* base, int warp, int ng) {
+// The view is rebuilt from the dynamic shared-memory symbol inside every function that needs it, so that the
+// accesses stay LDS/STS (a struct of pointers handed to an out-of-line function decays to generic LD/ST).
+__device__ __forceinline__ WarpMem warp_mem(int warp, int ng) {
+    extern __shared__ __align__(16) unsigned char mcs_smem[];
     WarpMem w;
-    unsigned char* p = base + (size_t)warp * warp_smem_bytes(ng);
+    unsigned char* p = mcs_smem + zone_tab_bytes(ng) + (size_t)warp * warp_smem_bytes(ng);
     w.part = reinterpret_cast<double*>(p);
-    double* q = w.part + 4 * ng + SC_N;
-    w.q_pb = q; w.q_pperp = q + QCAP; w.q_gam = q + 2 * QCAP; w.q_phi = q + 3 * QCAP; w.q_w = q + 4 * QCAP;
-    w.q_ptot = q + 5 * QCAP;
-    int* qi = reinterpret_cast<int*>(q + 6 * QCAP);
+    double* q = w.part + 3 * ng + SC_N;
+    w.q_pb = q; w.q_pperp = q + QCAP; w.q_gam = q + 2 * QCAP; w.q_cphi = q + 3 * QCAP; w.q_sphi = q + 4 * QCAP;
+    w.q_w = q + 5 * QCAP; w.q_ptot = q + 6 * QCAP;
+    int* qi = reinterpret_cast<int*>(q + 7 * QCAP);
     w.q_inew = qi; w.q_iold = qi + QCAP; w.q_iz = qi + 2 * QCAP;
     w.q_flags = reinterpret_cast<uint32_t*>(qi + 3 * QCAP);
     return w;
+}
+struct ZoneTab { const double2 *a, *b, *c; const double* gd; const double2* az; };  // {ux, gsf} | {gef, cos th} | {xg[i], xg[i+1]} | 1/(zz*btot) | azimuth
+__device__ __forceinline__ ZoneTab zone_tab(int ng) {
+    extern __shared__ __align__(16) unsigned char mcs_smem[];
+    ZoneTab z;
+    z.a = reinterpret_cast<const double2*>(mcs_smem);
+    z.b = z.a + (ng + 2); z.c = z.b + (ng + 2);
+    z.gd = reinterpret_cast<const double*>(z.c + (ng + 2));
+    z.az = reinterpret_cast<const double2*>(mcs_smem + zone_tab_bytes(ng) - (size_t)AZ_N * 16);
+    return z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -325,6 +356,21 @@ __device__ __forceinline__ void transform_p_PS(const DevParams& P, double pb, do
     gam_sk = hypot(ptot_sk / P.mc, 1.0);
 }
 
+// the same with the gyro-phase given as (cos phi, sin phi): sin(phi + pi/2) = cos phi, cos(phi + pi/2) = -sin phi
+__device__ __forceinline__ void transform_p_PS_cs(const DevParams& P, double pb, double pperp, double gam_pf, double cphi,
+                                                  double sphi, double ux, double gsf, double bcos, double bsin, double& ptot_sk,
+                                                  double& sx, double& sz, double& gam_sk) {
+    const double p_p_cos = pperp * -sphi;
+    const double fx = pb * bcos - p_p_cos * bsin;
+    const double fy = pperp * cphi;
+    const double fz = pb * bsin + p_p_cos * bcos;
+    const double dpx = (gsf - 1) * fx + gsf * gam_pf * P.m * ux;
+    sx = fx + dpx;
+    sz = fz;
+    ptot_sk = norm3(sx, fy, sz);
+    gam_sk = hypot(ptot_sk / P.mc, 1.0);
+}
+
 // pmax test of particle_loop.jl:262-275 (cold: only above pmax_cutoff)
 __device__ __noinline__ bool above_pmax_shock_frame(const DevParams& P, double pb, double pperp, double gam_pf, double phi,
                                                     int iz) {
@@ -384,6 +430,48 @@ __device__ __noinline__ Mom transform_p_PSP(const DevParams& P, int io, int in, 
     return mo;
 }
 
+// The same boost with the gyro-phase carried as (cos phi, sin phi) — the fast loop's representation.  The reference's
+// sincos(phi + pi/2) is (cos phi, -sin phi), and its new phase atan(ny, d) - pi/2 has cosine ny / h and sine -d / h with
+// h = hypot(ny, d): no trigonometric call at all.
+struct MomCS { double ptot, pb, pperp, gam_pf, cphi, sphi; };
+__device__ __noinline__ MomCS transform_p_PSP_cs(const DevParams& P, int io, int in, MomCS mi) {
+    const double pb = mi.pb, pperp = mi.pperp, gam_pf = mi.gam_pf;
+    const double ux_o = P.ux[io], uz_o = P.uz[io], gsf_o = P.gsf[io], bcos_o = P.costh[io], bsin_o = P.sinth[io];
+    const double ux = P.ux[in], uz = P.uz[in], gsf = P.gsf[in], bcos = P.costh[in], bsin = P.sinth[in];
+    const double p_p_cos = pperp * -mi.sphi;
+    const double fx = pb * bcos_o - p_p_cos * bsin_o;
+    const double fy = pperp * mi.cphi;
+    const double fz = pb * bsin_o + p_p_cos * bcos_o;
+    const double rxo = P.rxt[io], rzo = P.rzt[io], cro = P.crt[io];
+    const double sx = ((gsf_o - 1) * (rxo * rxo) + 1) * fx + (gsf_o - 1) * cro * fz + gsf_o * gam_pf * P.m * ux_o;
+    const double sy = fy;
+    const double sz = (gsf_o - 1) * cro * fx + ((gsf_o - 1) * (rzo * rzo) + 1) * fz + gsf_o * gam_pf * P.m * uz_o;
+    const double ptot_sk = norm3(sx, sy, sz);
+    const double pb_sk = sx * bcos + sz * bsin;
+    if (ptot_sk < fabs(pb_sk)) count(P, CNT_W_PPERP);
+    const double gam_sk = hypot(ptot_sk / P.mc, 1.0);
+    const double rx = P.rxt[in], rz = P.rzt[in], cr = P.crt[in];
+    const double nx = ((gsf - 1) * (rx * rx) + 1) * sx + (gsf - 1) * cr * sz - gsf * gam_sk * P.m * ux;
+    const double ny = sy;
+    const double nz = (gsf - 1) * cr * sx + ((gsf - 1) * (rz * rz) + 1) * sz - gsf * gam_sk * P.m * uz;
+    const double pt = norm3(nx, ny, nz);
+    double b = nx * bcos + nz * bsin, pp;
+    if (pt < fabs(b)) {
+        pp = 1.0e-6 * pt;
+        b = copysign(sqrt(pt * pt - pp * pp), b);
+        count(P, CNT_W_PPERP);
+    } else {
+        pp = sqrt(pt * pt - b * b);
+    }
+    MomCS mo;
+    mo.ptot = pt; mo.pb = b; mo.pperp = pp;
+    mo.gam_pf = hypot(pt / P.mc, 1.0);
+    const double d = -nx * bsin + nz * bcos, h = hypot(ny, d);
+    if (h > 0.0) { mo.cphi = ny / h; mo.sphi = -d / h; }
+    else { mo.cphi = 0.0; mo.sphi = -1.0; }  // atan(0, 0) = 0
+    return mo;
+}
+
 __device__ __forceinline__ double perpendicular_momentum(const DevParams& P, double ptot, double pb) {
     if (ptot < fabs(pb)) { count(P, CNT_W_PPERP); return 1.0e-6 * ptot; }
     return sqrt(ptot * ptot - pb * pb);
@@ -396,6 +484,7 @@ __device__ __forceinline__ double radiation_loss(const DevParams& P, double B2, 
 
 // cuts.jl:149-162
 __device__ __noinline__ void tcut_track(const DevParams& P, int tcut_curr, double weight, double ptot) {
+    count(P, CNT_RED, 2ull);
     red_add_f64(&P.t.w_coupled[tcut_curr - 1], weight);
     int ip = psd_bin_momentum(P, ptot);
     red_add_f64(&P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
@@ -419,6 +508,7 @@ __device__ __noinline__ Mom do_energy_transfer(const DevParams& P, int i_grid, i
         int n_split = 0;
         for (int i = i_start + 1; i <= i_stop; i++) n_split += P.eps_target[i - 1] > 0;
         double inc = (gam_i - gam_f) * E0 * weight / n_split;
+        count(P, CNT_RED, (unsigned long long)n_split);
         for (int i = i_start + 1; i <= i_stop; i++)
             if (P.eps_target[i - 1] > 0) red_add_f64(&P.t.pool[i - 1], inc);
         scale = true;
@@ -526,17 +616,18 @@ __device__ __noinline__ void bin_thermal_crossing(const DevParams& P, int lo, in
 //                     upstream-FEB scalars);
 //   finish event   -> particle_finish.jl:46-107 and the downstream sums of particle_loop.jl:478-495.
 // The n_grid-sized tallies and the scalars go to this warp's shared partials with plain adds in event order.
-__device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int base, int n_ev) {
+__device__ __noinline__ void process_events(const DevParams& P, int base, int n_ev) {
     const int lane = threadIdx.x & 31, ng = P.n_grid;
+    const WarpMem wm = warp_mem(threadIdx.x >> 5, ng);
     const bool act = lane < n_ev;
     const int q = base + (act ? lane : 0);
     const uint32_t fl = act ? wm.q_flags[q] : 0u;
-    const double pb = wm.q_pb[q], pperp = wm.q_pperp[q], gam_pf = wm.q_gam[q], phi = wm.q_phi[q], weight = wm.q_w[q],
-                 ptot = wm.q_ptot[q];
+    const double pb = wm.q_pb[q], pperp = wm.q_pperp[q], gam_pf = wm.q_gam[q], cphi = wm.q_cphi[q], sphi = wm.q_sphi[q],
+                 weight = wm.q_w[q], ptot = wm.q_ptot[q];
     const int i_new = wm.q_inew[q], i_old = wm.q_iold[q], iz = wm.q_iz[q];
     const double ux = P.ux[iz], gsf = P.gsf[iz], bcos = P.costh[iz], bsin = P.sinth[iz];
     double ptot_sk, sx, sz, gam_sk;
-    transform_p_PS(P, pb, pperp, gam_pf, phi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
+    transform_p_PS_cs(P, pb, pperp, gam_pf, cphi, sphi, ux, gsf, bcos, bsin, ptot_sk, sx, sz, gam_sk);
     const bool is_cross = (fl & EV_VALID) && !(fl & EV_FINISH), is_fin = (fl & EV_VALID) && (fl & EV_FINISH);
     const bool inj = fl & EV_INJ, up = fl & EV_UP;
     const double g0u0w = weight * P.gam0 * P.u0;  // reference order: value * weight * gam0 * u0 (kept below)
@@ -547,6 +638,7 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
     int lo = 1, hi = 0;
     double f_pxx = 0, f_pxz = 0, f_en = 0;
     bool thermal = false;
+    int n_red = 0;  // atomics this lane issues into the tallies (reported as the achieved atomic rate)
 
     if (is_cross) {
         double pt_o_px_sk, abs_inv_vx;
@@ -566,6 +658,7 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
             int ipt = psd_bin_momentum(P, ptot_sk), ipf = psd_bin_momentum(P, ptot);
             for (int i = 0; i < P.n_xspec; i++)
                 if (xmask & (1u << i)) {
+                    n_red += 2;
                     red_add_f64(&P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
                     double F = fabs(pb / sx) * (gam_sk / gam_pf);
                     red_add_f64(&P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
@@ -584,8 +677,10 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
                 const size_t stride = (size_t)(P.M + 2) * (size_t)(P.T + 2);
                 double* cell = P.t.psd + (size_t)ipt + (size_t)(P.M + 2) * (size_t)jth + stride * (size_t)(lo - 1);
                 for (int i = lo; i <= hi; i++, cell += stride) red_add_f64(cell, w);
+                n_red += hi - lo + 1;
             } else {
                 thermal = true;
+                n_red += hi - lo + 1;  // crossing counts
             }
         }
         if (fl & EV_FEB_UP) {  // :155-158
@@ -618,7 +713,7 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
                 if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
             }
         }
-        if (P.t.therm_sf != nullptr && nrec > 0) bin_thermal_crossing(P, lo, hi, sx, ptot_sk, gam_sk, ux, weight);
+        if (P.t.therm_sf != nullptr && nrec > 0) { bin_thermal_crossing(P, lo, hi, sx, ptot_sk, gam_sk, ux, weight); n_red += 2 * nrec; }
     }
     if (is_fin) {
         const int reason = (fl >> EV_REASON_SHIFT) & 7;
@@ -628,6 +723,7 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
             double wf;
             if (ptot_sk > fabs(SPIKE_AWAY * sx)) wf = gam_sk * P.m * SPIKE_AWAY / ptot_sk;
             else wf = gam_sk * (P.m / fabs(sx));
+            n_red += reason == 1 ? 1 : 3;
             if (reason == 1) {
                 red_add_f64(&P.t.esc_dn[ip + E1 * jt], weight * wf);
             } else {
@@ -661,8 +757,9 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
             wm.part[j - 1] += a;
             wm.part[ng + j - 1] += b;
             wm.part[2 * ng + j - 1] += c;
-            if (th) reinterpret_cast<unsigned long long*>(wm.part)[3 * ng + j - 1] += 1ull;
+            if (th) red_add_u64(&P.t.ncross[j - 1], 1ull);
         }
+        __syncwarp();  // the next event's lanes may touch the same cells: order the read-modify-write chain
     }
     bool any_sc = false;
 #pragma unroll
@@ -672,9 +769,11 @@ __device__ __noinline__ void process_events(const DevParams& P, WarpMem wm, int 
         for (int k = 0; k < SC_N - 1; k++) {
             double v = sc[k];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);  // fixed butterfly order
-            if (lane == 0) wm.part[4 * ng + k] += v;
+            if (lane == 0) wm.part[3 * ng + k] += v;
         }
     }
+    for (int o = 16; o > 0; o >>= 1) n_red += __shfl_xor_sync(FULL, n_red, o);
+    if (lane == 0 && n_red > 0) count(P, CNT_RED, (unsigned long long)n_red);
     __syncwarp();
 }
 
@@ -774,50 +873,81 @@ __device__ __noinline__ ColdIO reflect_loop(const DevParams& P, ColdIO io, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// The transport kernel.
+// Lane state.  The full record lives in local memory: the general section (out of line) works on a copy of it, the
+// fast loop keeps only what a plain pass needs in registers.  Splitting the kernel this way is what lets the fast loop
+// run at 64-80 registers (24-32 warps per SM): with the general pass inlined next to it the allocation was 128
+// registers with spills inside the loop (profiles/r01_v13_*).
+struct Lane {
+    double ptot, pb, pperp, x, prp_x, acct, phi;
+    double gam_pf, gd, grt, gr, gper, t_step, inv_ptot, inv_gm;
+    double ux, gsf, gef, bsin, bcos;
+    const double* rng_ru;
+    long long rng_rn;
+    int ip, next_j, iz, i_grid, i_grid_old, helix, tcut, i_return, xsel, slot, qn;
+    uint32_t rng_n, rng_s2, rng_s3, rng_c1;
+    bool rng_exhausted, queue_empty, down, inj, x_old_le0, parked;
+};
+
+// Converged: append the lanes' events (ev != 0) to the warp's queue, drain a full batch.  Returns the new queue length.
+__device__ __forceinline__ int push_events(const DevParams& P, const WarpMem& wm, int qn, uint32_t ev, int ip, double pb,
+                                           double pperp, double gam_pf, double cphi, double sphi, double ptot, int i_new,
+                                           int i_old, int iz) {
+    const unsigned m = __ballot_sync(FULL, ev != 0u);
+    if (m) {
+        const int cnt = __popc(m);
+        if (QCAP < 64 && qn + cnt > QCAP) {  // would not fit: drain what is queued as a partial batch first
+            __syncwarp();
+            process_events(P, 0, qn);
+            qn = 0;
+        }
+        if (ev) {
+            const int q = qn + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+            wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_cphi[q] = cphi; wm.q_sphi[q] = sphi;
+            wm.q_w[q] = P.cur.weight[ip];
+            wm.q_ptot[q] = ptot; wm.q_inew[q] = i_new; wm.q_iold[q] = i_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
+        }
+        qn += cnt;
+        if (qn >= 32) {  // sums commute; the order is fixed by the lock-step schedule
+            __syncwarp();
+            process_events(P, qn - 32, 32);
+            qn -= 32;
+        }
+    }
+    return qn;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General section: refill idle lanes, then run ONE full helix-loop pass (particle_loop.jl:154-499) for every lane that
+// asked for it (`parked`), including everything rare: escapes, pcut save, tcuts, energy transfer, reflection, probability
+// of return with retro_time, radiative losses, custom eps_B, replay/trace.  Repeats while lanes still need it (a particle
+// that finished is replaced at once; a particle back from retro_time gets its follow-up pass).  Returns true when the
+// warp has no particles left.  Configurations the fast loop cannot do (fast_ok false) never leave this function.
 template <bool DEBUG, bool ELECTRON>
-__global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(const __grid_constant__ DevParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__device__ __noinline__ bool general_section(const DevParams& P, Lane& Lref, const bool fast_ok) {
+    Lane l = Lref;
     const int ng = P.n_grid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const WarpMem wm = warp_mem(smem, warp, ng);
-    for (int i = lane; i < 4 * ng + SC_N; i += 32) wm.part[i] = 0.0;
-    __syncwarp();
-
+    const WarpMem wm = warp_mem(warp, ng);
     const uint32_t flags = P.flags;
     const bool custom = flags & F_CUSTOM_EPSB, dont_scatter = flags & F_DONT_SCATTER, dynamic = flags & F_DYNAMIC_QUEUE;
     const bool rad = ELECTRON && (flags & F_RAD_LOSSES);
-    // the fast loop covers scattering configurations without per-pass field updates, detectors or debug streams
-    const bool fast_ok = !DEBUG && !custom && !rad && !dont_scatter && P.n_xspec == 0 && !(flags & F_NO_FAST_LOOP);
     const long long total_warps = (long long)gridDim.x * n_warps, gwarp = (long long)blockIdx.x * n_warps + warp;
-
-    // lane state -------------------------------------------------------------------------------
-    // Kept small on purpose (128-register budget at 16 warps/SM): weight and a non-standard xn_per are re-read from
-    // the population arrays where needed, retro_time pass counts accumulate in P.retro[ip], x_old survives a pass only
-    // as the one bit Code Block 3 needs.
-    int ip = -1, next_j = 0;
-    bool queue_empty = false;
-    double ptot = 1, pb = 0, pperp = 0, x = 0, prp_x = 0, acct = 0, phi = 0;
-    double gam_pf = 1, gd = 0, grt = 0, gr = 0, gper = 0, t_step = 0, inv_ptot = 1, inv_gm = 1;
-    double ux = 0, gsf = 1, gef = 1, bsin = 0, bcos = 1;
-    int iz = 0, i_grid = 0, i_grid_old = 0, helix = 0, tcut = 1, i_return = -1, xsel = 0;
-    bool down = false, inj = false, x_old_le0 = true;
-    bool parked = true;  // the lane's next pass must take the general path (see the fast loop below)
-#ifdef MCS_SCHED_COUNTERS
-    unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_slow_sec = 0, c_slow_lane = 0;  // scheduling statistics
-#define MCS_SC(x) x
-#else
-#define MCS_SC(x)
-#endif
-    int qn = 0;  // events queued by this warp (warp-uniform)
-    Rng rng;  // only ever passed to force-inlined helpers from here: stays in registers
-    rng.n = 0; rng.s2 = rng.s3 = rng.c1 = 0; rng.ru = nullptr; rng.rn = 0; rng.exhausted = false;
-    int slot = -1;
+    int &ip = l.ip, &next_j = l.next_j, &iz = l.iz, &i_grid = l.i_grid, &i_grid_old = l.i_grid_old, &helix = l.helix,
+        &tcut = l.tcut, &i_return = l.i_return, &xsel = l.xsel, &slot = l.slot, &qn = l.qn;
+    double &ptot = l.ptot, &pb = l.pb, &pperp = l.pperp, &x = l.x, &prp_x = l.prp_x, &acct = l.acct, &phi = l.phi;
+    double &gam_pf = l.gam_pf, &gd = l.gd, &grt = l.grt, &gr = l.gr, &gper = l.gper, &t_step = l.t_step,
+           &inv_ptot = l.inv_ptot, &inv_gm = l.inv_gm;
+    double &ux = l.ux, &gsf = l.gsf, &gef = l.gef, &bsin = l.bsin, &bcos = l.bcos;
+    bool &queue_empty = l.queue_empty, &down = l.down, &inj = l.inj, &x_old_le0 = l.x_old_le0, &parked = l.parked;
+    Rng rng;
+    rng.n = l.rng_n; rng.s2 = l.rng_s2; rng.s3 = l.rng_s3; rng.c1 = l.rng_c1; rng.ru = l.rng_ru; rng.rn = l.rng_rn;
+    rng.exhausted = l.rng_exhausted;
+    bool all_done = false;
 
     for (;;) {
         // ---- refill idle lanes ---------------------------------------------------------------------
         unsigned need = __ballot_sync(FULL, ip < 0 && !queue_empty);
-        if (MCS_UNLIKELY(need != 0u)) {
+        if (need != 0u) {
             const int rank = __popc(need & ((1u << lane) - 1u));
             long long base;
             if (dynamic) {  // one atomic per warp on the global queue head
@@ -841,8 +971,11 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                     i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
                     down = P.cur.down[ip]; inj = P.cur.inj[ip];
                     helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0;
-                    parked = !fast_ok;  // a fresh particle needs nothing the fast loop cannot do
                     xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
+                    // A fresh particle needs nothing the fast loop cannot do, unless its record is outside what the
+                    // loop itself produces (hand-made populations): those take the general pass first.
+                    parked = !fast_ok || xsel > 1 || prp_x < P.x_grid_stop || (inj && x < P.feb_up) || (down && !inj && x < 0) ||
+                             i_grid > ng;
                     gam_pf = hypot(1.0, ptot / P.mc);
                     gd = 1 / (P.zz * P.bt[i_grid]);
                     if (custom && x > P.x_grid_stop) gd *= sqrt(x / P.x_grid_stop);
@@ -867,16 +1000,16 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 }
             }
         }
-        if (__all_sync(FULL, ip < 0)) break;
+        if (__all_sync(FULL, ip < 0)) { all_done = true; break; }
+        if (!__any_sync(FULL, ip >= 0 && parked)) break;  // nobody asks for the general pass: back to the fast loop
 
         // ---- one pass of the helix loop (particle_loop.jl:154-499) ------------------------------------
         int fin = -1;          // -1 running; 0 saved; 1..4 i_reason; 5 error
         uint32_t ev = 0;       // crossing event to queue at point A
         bool moved = false;
         double x_old = 0.0;    // position before this pass's move
-        MCS_SC(c_slow_sec++;)
-        if (ip >= 0 && parked) {
-            MCS_SC(c_slow_lane++;)
+        const bool served = ip >= 0 && parked;
+        if (served) {
             helix++;
             if (MCS_UNLIKELY(helix > P.helix_cap)) {
                 fin = 1;  // K-1
@@ -998,8 +1131,8 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 }
                 if (MCS_UNLIKELY(x_old < 0 && x >= 0)) {
                     down = true;
-                    double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
-                    prp_x = fmax(prp_x, L);
+                    double Ld = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
+                    prp_x = fmax(prp_x, Ld);
                 }
                 if (down && x < 0) inj = true;
                 i_grid_old = i_grid;
@@ -1040,20 +1173,9 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
         }
         // ---- point A (converged): queue the crossing events with the state as it is right after the move ----
         {
-            const unsigned m = __ballot_sync(FULL, ev != 0u);
-            if (m) {
-                if (ev) {
-                    const int q = qn + __popc(m & ((1u << lane) - 1u));
-                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = P.cur.weight[ip];
-                    wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
-                }
-                qn += __popc(m);
-            }
-        }
-        if (qn >= 32) {
-            __syncwarp();
-            process_events(P, wm, qn - 32, 32);
-            qn -= 32;
+            double ec = 1.0, es = 0.0;
+            if (ev) sincos_bf(phi, &es, &ec);
+            qn = push_events(P, wm, qn, ev, ip, pb, pperp, gam_pf, ec, es, ptot, i_grid, i_grid_old, iz);
         }
         // ---- rest of Code Block 2: downstream escape / return ------------------------------------------------
         bool sum_p = false;
@@ -1117,221 +1239,312 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             release = true;  // ip is still needed by the event push below (weight is read from the population array)
         }
         {
-            const unsigned m = __ballot_sync(FULL, ev != 0u);
-            if (m) {
-                if (ev) {
-                    const int q = qn + __popc(m & ((1u << lane) - 1u));
-                    wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi; wm.q_w[q] = P.cur.weight[ip];
-                    wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
-                }
-                qn += __popc(m);
-            }
+            double ec = 1.0, es = 0.0;
+            if (ev) sincos_bf(phi, &es, &ec);
+            qn = push_events(P, wm, qn, ev, ip, pb, pperp, gam_pf, ec, es, ptot, i_grid, i_grid_old, iz);
         }
         if (release) ip = -1;
-        if (qn >= 32) {  // drain a full batch (sums commute; the order is fixed by the lock-step schedule)
-            __syncwarp();
-            process_events(P, wm, qn - 32, 32);
-            qn -= 32;
-        }
-        parked = false;
-        // lanes whose particle just finished are refilled before the fast loop, not after it: they would idle through
-        // a whole residency (up to MCS_FAST_MAX iterations, a large share of a short trajectory)
-        if (fast_ok && __any_sync(FULL, ip < 0 && !queue_empty)) continue;
+        // a particle back from retro_time (i_return == 1) takes its follow-up pass here at once
+        if (served) parked = !fast_ok || (ip >= 0 && i_return == 1);
+    }
+    l.rng_n = rng.n; l.rng_s2 = rng.s2; l.rng_s3 = rng.s3; l.rng_c1 = rng.c1; l.rng_ru = rng.ru; l.rng_rn = rng.rn;
+    l.rng_exhausted = rng.exhausted;
+    Lref = l;
+    return all_done;
+}
 
-        // ---- FAST LOOP ------------------------------------------------------------------------------------------
-        // The bare arithmetic of a pass runs at 8e10 steps/s on B200 when it is a tight loop (scatter_only_kernel);
-        // the general pass above is ~2x the instructions spread over 32 KB of code and reaches IPC 0.3.  So passes in
-        // which NOTHING rare happens (no zone change, escape, save, tcut, reflection, shock crossing, PRP logic) are
-        // done here, in a loop small enough for the instruction cache.  A lane that meets anything rare commits
-        // nothing and PARKS; when MCS_PARK_T lanes are waiting the warp goes round the outer loop once and the
-        // general pass serves all of them together.  Per particle the sequence of operations is unchanged.
-        if (fast_ok) {
-            bool need_psp = false;  // the lane stands at a zone change that needs a boost and waits for company (below)
-            int psp_debt = 0;       // lane-iterations spent waiting since the last batch of boosts (warp-uniform)
-#if MCS_WAIT_DEBT > 0
-            int wait_debt = 0;
+// lane status bits of the fast loop
+enum : uint32_t {
+    ST_DOWN = 1u, ST_INJ = 2u, ST_XOLDLE0 = 4u, ST_PARKED = 8u, ST_NEEDPSP = 16u, ST_XSEL = 32u, ST_GTPMAX = 64u, ST_GTPCUT = 128u,
+    ST_RAN = 256u,   // at least one fast pass committed in this residency (i_return = 2)
+    ST_MUSN = 512u,  // mu / sn are newer than the record's pb / pperp
+    ST_PHI = 1024u,  // the phase registers are newer than the record's angle (a boost without a committed pass after it)
+};
+
+// sin and cos of the scattering azimuth phi_s = 2 pi u - pi (scattering.jl:71) for u = w / 2^53, w the 53-bit random
+// integer (hi:lo >> 11): the top 8 bits of w pick a table entry {sin A_k, cos A_k}, A_k = -pi + 2 pi (k + 1/2) / 256, the
+// other 45 bits the offset |t| <= pi/256 from it, whose sine and cosine need three terms each; angle addition.  12 FP64
+// operations and 6 constants instead of 26 and 16 for a general sincos; error <= 1.5 ulp of 1.
+__device__ __forceinline__ void az_sincos(const double2* __restrict__ tab, uint32_t hi, uint32_t lo, double& s_out, double& c_out) {
+    const uint32_t k = hi >> 24;
+    // f = bits 44..0 of w: bits 23..11 of hi (13 bits) above bits 31..11 of lo... as an exact double via the 2^52 trick
+    const uint32_t f_hi = (hi >> 11) & 0x1fffu;             // bits 44..32 of f
+    const uint32_t f_lo = (lo >> 11) | (hi << 21);          // bits 31..0 of f
+    const double f = __hiloint2double((int)(0x43300000u | f_hi), (int)f_lo) - 4503599627370496.0;  // exact: f < 2^45
+    const double t = fma(f, 6.975736996017264e-16, -0.01227184630308513);  // 2 pi / 256 / 2^45 * f - pi / 256
+    const double z = t * t;
+    const double ps = fma(z, 0.008333333333333333, -0.16666666666666666);
+    const double st = fma(t * z, ps, t);
+    double pc = fma(z, -0.001388888888888889, 0.041666666666666664);
+    pc = fma(z, pc, -0.5);
+    const double ct = fma(z, pc, 1.0);
+    const double2 e = tab[k];
+    s_out = fma(e.x, ct, e.y * st);
+    c_out = fma(e.y, ct, -(e.x * st));
+}
+
+// Base.mod2pi for -2pi < v < 4pi without branches (the general formula with k = -1, 0, 1 and the same roundings);
+// ok = false when the result needs the final wrap of the general formula or v is outside that range: the lane parks.
+__device__ __forceinline__ double mod2pi_bf(double v, bool& ok) {
+    const double kd = v >= TWO_PI ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
+    double r = fma(-kd, TWO_PI, v);
+    r = fma(-kd, TWO_PI_LO, r);
+    ok = (r >= 0.0) & (r < TWO_PI);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The transport kernel.
+template <bool DEBUG, bool ELECTRON>
+__global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(const __grid_constant__ DevParams P) {
+    extern __shared__ __align__(16) unsigned char mcs_smem[];
+    const int ng = P.n_grid;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    {   // zone table of the fast loop
+        double2* za = reinterpret_cast<double2*>(mcs_smem);
+        double2 *zb = za + (ng + 2), *zc = zb + (ng + 2);
+        double* zd = reinterpret_cast<double*>(zc + (ng + 2));
+        for (int i = threadIdx.x; i < ng + 2; i += blockDim.x) {
+            za[i] = make_double2(P.ux[i], P.gsf[i]);
+            zb[i] = make_double2(P.gef[i], P.costh[i]);
+            zc[i] = make_double2(P.xg[i], i <= ng ? P.xg[i + 1] : __longlong_as_double(0x7ff0000000000000ll));
+            zd[i] = 1 / (P.zz * P.bt[i]);
+        }
+        double2* az = reinterpret_cast<double2*>(mcs_smem + zone_tab_bytes(ng) - (size_t)AZ_N * 16);
+        for (int i = threadIdx.x; i < AZ_N; i += blockDim.x) az[i] = P.az_tab[i];
+    }
+    const WarpMem wm = warp_mem(warp, ng);
+    for (int i = lane; i < 3 * ng + SC_N; i += 32) wm.part[i] = 0.0;
+    __syncthreads();
+    const ZoneTab zt = zone_tab(ng);
+
+    const uint32_t flags = P.flags;
+    // the fast loop covers scattering configurations without per-pass field updates, detectors or debug streams
+    const bool fast_ok = !DEBUG && !(flags & (F_CUSTOM_EPSB | F_DONT_SCATTER | F_NO_FAST_LOOP)) &&
+                         !(ELECTRON && (flags & F_RAD_LOSSES)) && P.n_xspec == 0;
+    const bool reflect_cfg = (flags & F_DONT_DSA) || P.inj_frac < 1;
+
+    Lane L;
+    L.ptot = 1; L.pb = 0; L.pperp = 0; L.x = 0; L.prp_x = 0; L.acct = 0; L.phi = 0;
+    L.gam_pf = 1; L.gd = 0; L.grt = 0; L.gr = 0; L.gper = 0; L.t_step = 0; L.inv_ptot = 1; L.inv_gm = 1;
+    L.ux = 0; L.gsf = 1; L.gef = 1; L.bsin = 0; L.bcos = 1;
+    L.rng_ru = nullptr; L.rng_rn = 0;
+    L.ip = -1; L.next_j = 0; L.iz = 0; L.i_grid = 0; L.i_grid_old = 0; L.helix = 0; L.tcut = 1; L.i_return = -1; L.xsel = 0;
+    L.slot = -1; L.qn = 0;
+    L.rng_n = 0; L.rng_s2 = 0; L.rng_s3 = 0; L.rng_c1 = 0;
+    L.rng_exhausted = false; L.queue_empty = false; L.down = false; L.inj = false; L.x_old_le0 = true; L.parked = true;
+#ifdef MCS_SCHED_COUNTERS
+    unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_sections = 0;
+#define MCS_SC(x) x
+#else
+#define MCS_SC(x)
 #endif
+
+    for (;;) {
+        MCS_SC(c_sections++;)
+        if (general_section<DEBUG, ELECTRON>(P, L, fast_ok)) break;
+        if constexpr (!DEBUG) {
+            // ---- FAST LOOP -------------------------------------------------------------------------------------
+            // Passes in which nothing rare happens (scatter, move, zone search, zone change without a boost, shock
+            // crossing, PRP placement, the crossing event).  A lane that meets anything else commits nothing and PARKS;
+            // when enough lanes wait, the warp leaves for the general section.  Per particle the sequence of operations
+            // is the one of particle_loop.jl.  Register state: position, pitch (mu, sn = pb, pperp over ptot), phase,
+            // clock, PRP, and three per-momentum constants; zone constants come from the shared zone table.
+            const int ip = L.ip;
+            const bool live = ip >= 0;  // after the general section every lane with a particle runs
+            double x = L.x, acct = L.acct, prp_x = L.prp_x, grt = L.grt, t_step = L.t_step;
+            double mu = L.pb * L.inv_ptot, sn = L.pperp * L.inv_ptot;
+            double vgm = L.ptot * L.inv_gm;
+            double gper = (ELECTRON && L.ptot < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * L.gd : TWO_PI * L.gam_pf * P.mc * L.gd;
+            double cph, sph;  // gyro-phase as (cos, sin): the kick and the advance are rotations, no asin / mod2pi per pass
+            sincos(L.phi, &sph, &cph);
+            int iz = L.iz, helix = L.helix, qn = L.qn;
+            uint32_t gpack = (uint32_t)L.i_grid | ((uint32_t)L.i_grid_old << 16);
+            uint32_t rng_n = L.rng_n, rng_s2 = L.rng_s2, rng_s3 = L.rng_s3;
+            const uint32_t rng_c1 = L.rng_c1;
+            uint32_t st = (L.down ? ST_DOWN : 0u) | (L.inj ? ST_INJ : 0u) | (L.x_old_le0 ? ST_XOLDLE0 : 0u) | (L.xsel ? ST_XSEL : 0u) |
+                          (L.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) | (L.ptot > P.pcut ? ST_GTPCUT : 0u);
+            const int n_act = __popc(__ballot_sync(FULL, live));
+            const int park_t = min(MCS_PARK_T, (3 * n_act + 3) >> 2);
+            int psp_debt = 0, wait_debt = 0;
             for (int it = 0; it < MCS_FAST_MAX; it++) {
-                uint32_t fev = 0;  // crossing event produced by this fast pass
-                if (ip >= 0 && !parked && !need_psp) {
-                    bool park = (helix >= P.helix_cap) | (i_return == 1) | (xsel > 1) |
-                                (P.energy_transfer_frac > 0 && !inj && x_old_le0 && i_grid_old != i_grid) |
-                                (ptot > P.pmax_cutoff) | (inj && x < P.feb_up) | (P.age_max > 0 && acct > P.age_max);
-                    if (i_grid != iz && !park) {
-                        // Code Block 3 zone change (particle_loop.jl:186-228).  Without a change of flow speed it is a
-                        // reload of the zone's constants; with one, the momentum must be boosted (transform_p_PSP, ~350
-                        // instructions out of line).  In a smoothed precursor about one lane per iteration needs that,
-                        // so boosts are served in batches after the pass instead of one lane at a time.
-                        if (P.ux[i_grid] != ux) need_psp = true;
+                uint32_t fev = 0;   // crossing event produced by this pass
+                int ev_old = 0;     // its zone before the move
+                if (live && !(st & (ST_PARKED | ST_NEEDPSP))) {
+                    const int ig = (int)(gpack & 0xffffu);
+                    // what the general pass must see before this pass: helix cap, a momentum above a cut-off, pending energy
+                    // transfer, age
+                    uint32_t park = (helix >= P.helix_cap) ? 1u : 0u;
+                    park |= st & ST_GTPMAX;
+                    park |= ((st & (ST_DOWN | ST_GTPCUT)) == (ST_DOWN | ST_GTPCUT)) ? 1u : 0u;
+                    if (P.energy_transfer_frac > 0) park |= ((st & (ST_INJ | ST_XOLDLE0)) == ST_XOLDLE0 && (int)(gpack >> 16) != ig) ? 1u : 0u;
+                    if (P.age_max > 0) park |= (acct > P.age_max) ? 1u : 0u;
+                    if (ig != iz && !park) {
+                        // Code Block 3 zone change (particle_loop.jl:186-228): without a change of flow speed only the
+                        // zone's constants change; with one, the momentum must be boosted (batched below)
+                        if (zt.a[ig].x != zt.a[iz].x) st |= ST_NEEDPSP;
                         else {
-                            iz = i_grid;
-                            gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
-                            gd = 1 / (P.zz * P.bt[iz]);
+                            const double gd_n = zt.gd[ig];
+                            if (gd_n != zt.gd[iz])
+                                gper = (ELECTRON && L.ptot < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * gd_n : TWO_PI * L.gam_pf * P.mc * gd_n;
+                            iz = ig;
                         }
                     }
-                  if (!need_psp) {
-                    double acct_n = acct;
-                    if (down) {
-                        acct_n = acct + t_step * gef;
-                        park |= ((flags & F_TCUTS) && tcut <= P.n_tcuts && acct_n >= P.tcuts[tcut - 1]) | (ptot > P.pcut);
-                    }
-#ifdef MCS_PARK_REASONS
-                    if (park) {
-                        int why = helix >= P.helix_cap ? 0 : i_return == 1 ? 1 : (i_grid != iz && P.ux[i_grid] != ux) ? 2 :
-                                  (ptot > P.pmax_cutoff) ? 3 : (inj && x < P.feb_up) ? 4 : (down && ptot > P.pcut) ? 5 : 6;
-                        count(P, CNT_PARK0 + why);
-                    }
-#endif
-                    if (!park) {
-                        // scattering.jl:29-101 (same expressions as the general pass)
-                        double gper_n;
-                        if (ELECTRON && ptot < P.pe_crit) gper_n = TWO_PI * P.gam_e_crit * P.mc * gd;
-                        else gper_n = TWO_PI * gam_pf * P.mc * gd;
-                        const double omc = P.omc[xsel];
-                        // one Philox block per pass whether or not the stream is block-aligned
-                        const uint32_t odd = rng.n & 1u;
-                        uint32_t o0, o1, o2, o3;
-                        philox4x32_10_rk((rng.n + odd) >> 1, rng.c1, P.ctr2, P.ctr3, P.rk, o0, o1, o2, o3);
-                        const double u1 = odd ? u53(rng.s3, rng.s2) : u53(o1, o0);
-                        const double u2 = odd ? u53(o1, o0) : u53(o3, o2);
-                        const double cos_old = pb * inv_ptot, sin_old = pperp * inv_ptot;
-                        const double cos_d = 1 - u1 * omc;
-                        const double sd2 = 1 - cos_d * cos_d;
-                        const double phi_s = u2 * TWO_PI - PI;
-                        double sps, cps;
-                        sincos_bf(phi_s, &sps, &cps);
-                        // sqrt_nr/div_nr: NaN for sd2 == 0 or sn2 <= 0 -> sn2 / x_n turn NaN -> the lane parks below
-                        const double sin_d = sqrt_nr(sd2);
-                        const double cos_new = cos_old * cos_d + sin_old * sin_d * cps;
-                        const double sn2 = 1 - cos_new * cos_new;
-                        const double sin_new = sqrt_nr(sn2);
-                        double phi_p = phi + HALF_PI;
-                        {
+                    if (!(st & ST_NEEDPSP)) {
+                        const double2 za = zt.a[iz], zb = zt.b[iz], zc = zt.c[iz];  // {ux, gsf} {gef, cos th} {xg[iz], xg[iz+1]}
+                        double acct_n = acct;
+                        if (st & ST_DOWN) {
+                            acct_n = acct + t_step * zb.x;
+                            if (flags & F_TCUTS) park |= (L.tcut <= P.n_tcuts && acct_n >= P.tcuts[L.tcut - 1]) ? 1u : 0u;
+                        }
+                        if (!park) {
+                            // scattering.jl:29-101: same kick as the general pass; the azimuth's sine and cosine come
+                            // from the table, the phase change asin(s) is applied as the rotation (sqrt(1 - s^2), s)
+                            const double omc = P.omc[(st & ST_XSEL) ? 1 : 0];
+                            // one Philox block per pass whether or not the stream is block-aligned
+                            const uint32_t odd = rng_n & 1u;
+                            uint32_t o0, o1, o2, o3;
+                            philox4x32_10_rk((rng_n + odd) >> 1, rng_c1, P.ctr2, P.ctr3, P.rk, o0, o1, o2, o3);
+                            const double u1 = odd ? u53(rng_s3, rng_s2) : u53(o1, o0);
+                            double sps, cps;
+                            az_sincos(zt.az, odd ? o1 : o3, odd ? o0 : o2, sps, cps);
+                            const double cos_d = 1 - u1 * omc;
+                            const double sd2 = 1 - cos_d * cos_d;
+                            // sqrt_nr/div_nr: NaN for sd2 == 0 or sn2 <= 0 -> sn2 turns NaN -> the lane parks below
+                            const double sin_d = sqrt_nr(sd2);
+                            const double cos_new = mu * cos_d + sn * sin_d * cps;
+                            const double sn2 = 1 - cos_new * cos_new;
+                            const double sin_new = sqrt_nr(sn2);
                             double sv = div_nr(sps * sin_d, sin_new);
                             if (fabs(sv) > SIN_UPPER_LIMIT) sv = copysign(SIN_UPPER_LIMIT, sv);
-                            phi_p += asin_bf<true>(sv);
-                        }
-                        const double phi_sc = phi_p - HALF_PI;
-                        const double pb_n = ptot * cos_new, pperp_n = ptot * sin_new;
-                        // Code Block 2 move
-                        const int xsel_n = x > grt ? 1 : 0;
-                        const double t_n = gper_n * P.inv_xn[xsel_n];
-                        const double phi_n = mod2pi(phi_sc + P.dphi[xsel_n]);
-                        const double x_move = pb_n * t_n * inv_gm;
-                        const double gyr = MCS_UNLIKELY(bsin != 0.0) ? gr * bsin * (cos_bf(phi_n) - cos_bf(phi_sc)) : 0.0;
-                        const double x_n = x + gsf * (x_move * bcos - gyr + ux * t_n);
-                        // anything the general pass would have to act on after the move -> nothing is committed
-                        park = !(sd2 >= 0.0) | !(sn2 > 0.0) | !(x_n == x_n) |
-                               (x_n <= 0 && x > 0 && !inj && ((flags & F_DONT_DSA) || P.inj_frac < 1)) |
-                               (P.feb_dn > 0 && x_n > P.feb_dn);
-                        double prp_n = prp_x;
-                        const bool cross_down = x < 0 && x_n >= 0;
-                        if (cross_down) {  // particle_loop.jl:413-429: first/next arrival downstream, make the region long enough
-                            const double L = P.eta_mfp / 3 * grt * ptot / (P.m * gam_pf * P.u2);
-                            prp_n = fmax(prp_x, L);
-                        }
-                        if (x_n > 1.1 * prp_n) {
-                            // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes only beyond 6.91 L_diff
-                            double v_fac;
-                            if (ELECTRON && ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * gd) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
-                            else v_fac = grt * ptot / (P.m * gam_pf * P.u2);
-                            park |= x_n > 6.91 * (P.eta_mfp / 3 * v_fac);
-                        }
-                        if (x_n >= P.x_grid_stop) {
-                            if (x < P.x_grid_stop) {
-                                // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP (custom eps_B is never here)
-                                const double g2 = ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
-                                prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * ptot / (P.aa * P.mp * gam_pf * P.u2));
-                            } else {
-                                park |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
+                            const double cv = sqrt_nr(1 - sv * sv);  // cos(asin(sv)) >= 0
+                            const double c1 = cph * cv - sph * sv, s1 = sph * cv + cph * sv;
+                            // Code Block 2 move
+                            const bool xs_n = x > grt;
+                            const int xi = xs_n ? 1 : 0;
+                            const double t_n = gper * P.inv_xn[xi];
+                            const double cd = P.cdphi[xi], sd = P.sdphi[xi];
+                            const double cph_n = c1 * cd - s1 * sd, sph_n = s1 * cd + c1 * sd;
+                            const double x_move = (cos_new * vgm) * t_n;
+                            double gyr = 0.0;
+                            if (P.oblique) {
+                                const double bsin = P.sinth[iz];
+                                if (bsin != 0.0) gyr = L.gr * bsin * (cph_n - c1);
                             }
-                        }
-#ifdef MCS_PARK_REASONS
-                        if (park) {
-                            int why = (x < 0 && x_n >= 0) ? 8 :
-                                      (x_n >= P.x_grid_stop && x < P.x_grid_stop) ? 10 : (x < prp_x && x_n >= prp_x) ? 11 :
-                                      (x_n > 1.1 * prp_x) ? 12 : (x_n <= 0 && x > 0 && !inj) ? 13 : 14;
-                            count(P, CNT_PARK0 + why);
-                        }
-#endif
-                        if (!park) {
-                            // zone search (all_flux.jl:65-82) and the crossing event
+                            const double x_n = x + za.y * (x_move * zb.y - gyr + za.x * t_n);
+                            // Is this a plain pass?  Same zone, and inside the grid or between its end and the PRP.
                             const bool dn = x_n > x;
-                            int ig = i_grid;
-                            const double edge = P.xg[i_grid + (dn ? 1 : 0)];
-                            if (!(dn ? (edge > x_n) : (edge <= x_n))) {
-                                if (dn) { int k = i_grid + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig = k - 1; }
-                                else { int k = i_grid; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig = k; }
+                            const bool same = dn ? (zc.y > x_n) : (zc.x <= x_n);
+                            bool rare = !same | !(sn2 > 0.0) | !(cph_n == cph_n) |
+                                        ((x_n >= P.x_grid_stop) & ((x < P.x_grid_stop) | (x_n >= prp_x) | ELECTRON));
+                            if (st & ST_INJ) rare |= x_n < P.feb_up;
+                            if (P.feb_dn > 0) rare |= x_n > P.feb_dn;
+                            if (reflect_cfg) rare |= (x_n <= 0) & (x > 0);
+                            int ig_new = iz;
+                            double prp_n = prp_x;
+                            uint32_t st_n = st;
+                            bool go = true;
+                            if (rare) {
+                                // anything the general pass would have to act on after the move -> nothing is committed
+                                bool pk = !(sn2 > 0.0) | !(cph_n == cph_n) | !(x_n == x_n) |
+                                          (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) | (P.feb_dn > 0 && x_n > P.feb_dn);
+                                const bool cross_down = x < 0 && x_n >= 0;
+                                if (cross_down) {  // particle_loop.jl:413-429: arrival downstream, make the region long enough
+                                    const double Ld = P.eta_mfp / 3 * grt * L.ptot / (P.m * L.gam_pf * P.u2);
+                                    prp_n = fmax(prp_x, Ld);
+                                }
+                                if (x_n > 1.1 * prp_n) {
+                                    // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes beyond 6.91 L_diff
+                                    double v_fac;
+                                    if (ELECTRON && L.ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * zt.gd[iz]) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
+                                    else v_fac = grt * L.ptot / (P.m * L.gam_pf * P.u2);
+                                    pk |= x_n > 6.91 * (P.eta_mfp / 3 * v_fac);
+                                }
+                                if (x_n >= P.x_grid_stop) {
+                                    if (x < P.x_grid_stop) {
+                                        // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP
+                                        const double g2 = L.ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
+                                        prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * L.ptot / (P.aa * P.mp * L.gam_pf * P.u2));
+                                    } else {
+                                        pk |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
+                                    }
+                                }
+                                if (!pk) {
+                                    // zone search (all_flux.jl:65-82) and the crossing event
+                                    if (!same) {
+                                        if (dn) { int k = iz + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig_new = k - 1; }
+                                        else { int k = iz; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig_new = k; }
+                                    }
+                                    if (cross_down) st_n |= ST_DOWN;
+                                    if ((st_n & ST_DOWN) && x_n < 0) st_n |= ST_INJ;  // particle_loop.jl:433-435 (before all_flux)
+                                    const bool below_feb = (st_n & ST_INJ) && x_n < P.feb_up;
+                                    const bool feb_x = below_feb && x >= P.feb_up;
+                                    if (ig_new != iz || (feb_x && ig_new <= P.i_grid_feb))
+                                        fev = EV_VALID | ((st_n & ST_INJ) ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
+                                    if (below_feb) st_n |= ST_PARKED;  // the next pass ends at the upstream FEB: general pass
+                                }
+                                go = !pk;
                             }
-                            if (cross_down) down = true;
-                            if (down && x_n < 0) inj = true;  // particle_loop.jl:433-435 (before all_flux)
-                            const bool feb_x = inj && x_n < P.feb_up && x >= P.feb_up;
-                            if (ig != i_grid || (feb_x && ig <= P.i_grid_feb))
-                                fev = EV_VALID | (inj ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
-                            prp_x = prp_n;
-                            helix++; MCS_SC(c_fast_lane++;)
-                            acct = acct_n; gper = gper_n; t_step = t_n; xsel = xsel_n;
-                            pb = pb_n; pperp = pperp_n; phi = phi_n;
-                            x_old_le0 = x <= 0.0; x = x_n; i_grid_old = i_grid; i_grid = ig; i_return = 2;
-                            rng.n += 2; rng.s2 = o2; rng.s3 = o3;
+                            if (go) {
+                                ev_old = iz;
+                                st = (st_n & ~(ST_XOLDLE0 | ST_XSEL)) | (x <= 0.0 ? ST_XOLDLE0 : 0u) | (xs_n ? ST_XSEL : 0u) | ST_RAN | ST_MUSN;
+                                prp_x = prp_n;
+                                helix++; MCS_SC(c_fast_lane++;)
+                                acct = acct_n; t_step = t_n;
+                                mu = cos_new; sn = sin_new; cph = cph_n; sph = sph_n; x = x_n;
+                                gpack = (uint32_t)ig_new | ((uint32_t)iz << 16);
+                                rng_n += 2; rng_s2 = o2; rng_s3 = o3;
+                            } else {
+                                park = 1u;
+                            }
                         }
-                    }
-                    parked = park;
-                  }
-                }
-                {   // converged: queue the crossing events of this fast pass (state right after the move, as at point A)
-                    const unsigned m = __ballot_sync(FULL, fev != 0u);
-                    if (m) {
-                        if (fev) {
-                            const int q = qn + __popc(m & ((1u << lane) - 1u));
-                            wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_phi[q] = phi;
-                            wm.q_w[q] = P.cur.weight[ip]; wm.q_ptot[q] = ptot; wm.q_inew[q] = i_grid; wm.q_iold[q] = i_grid_old;
-                            wm.q_iz[q] = iz; wm.q_flags[q] = fev;
-                        }
-                        qn += __popc(m);
-                        if (qn >= 32) {
-                            __syncwarp();
-                            process_events(P, wm, qn - 32, 32);
-                            qn -= 32;
-                        }
+                        if (park) st |= ST_PARKED;
                     }
                 }
-                {   // converged: pending boosts.  Waiting costs idle lanes, serving costs the whole warp ~350 issue slots:
+                // converged: queue the crossing events of this pass (state right after the move, as at point A)
+                if (__any_sync(FULL, fev != 0u))
+                    qn = push_events(P, wm, qn, fev, ip, L.ptot * mu, L.ptot * sn, L.gam_pf, cph, sph, L.ptot, (int)(gpack & 0xffffu), ev_old,
+                                     ev_old);
+                {   // converged: pending boosts.  Waiting costs idle lanes, serving costs the whole warp ~250 issue slots:
                     // serve once the lanes have waited MCS_PSP_DEBT lane-iterations in total, or when fewer lanes run
                     // than wait.
-                    const unsigned mp = __ballot_sync(FULL, need_psp);
+                    const unsigned mp = __ballot_sync(FULL, (st & ST_NEEDPSP) != 0u);
                     if (mp) {
                         const int n_psp = __popc(mp);
-                        const int n_run = __popc(__ballot_sync(FULL, ip >= 0 && !parked && !need_psp));
+                        const int n_run = __popc(__ballot_sync(FULL, live && !(st & (ST_PARKED | ST_NEEDPSP))));
                         psp_debt += n_psp;
                         if (psp_debt >= MCS_PSP_DEBT || MCS_PSP_NUM * n_psp >= n_run) {
                             psp_debt = 0;
-                            if (need_psp) {
-                                need_psp = false;
+                            if (st & ST_NEEDPSP) {
+                                st &= ~ST_NEEDPSP;
                                 const int iz_old = iz;
-                                iz = i_grid;
-                                ux = P.ux[iz];
-                                gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
-                                gd = 1 / (P.zz * P.bt[iz]);
-                                Mom mi;
-                                mi.ptot = ptot; mi.pb = pb; mi.pperp = pperp; mi.gam_pf = gam_pf; mi.phi = phi;
-                                const Mom mo = transform_p_PSP(P, iz_old, iz, mi);
-                                ptot = mo.ptot; pb = mo.pb; pperp = mo.pperp; gam_pf = mo.gam_pf; phi = mo.phi;
-                                gr = pperp * P.c * gd;
-                                grt = ptot * P.c * gd;
-                                inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
-                                // the boosted momentum may now exceed a cut-off: let the general pass decide
-                                parked = (ptot > P.pmax_cutoff) | (down && ptot > P.pcut);
+                                iz = (int)(gpack & 0xffffu);
+                                const double gd = zt.gd[iz];
+                                MomCS mi;
+                                mi.ptot = L.ptot; mi.gam_pf = L.gam_pf; mi.cphi = cph; mi.sphi = sph;
+                                mi.pb = (st & ST_MUSN) ? L.ptot * mu : L.pb;
+                                mi.pperp = (st & ST_MUSN) ? L.ptot * sn : L.pperp;
+                                const MomCS mo = transform_p_PSP_cs(P, iz_old, iz, mi);
+                                cph = mo.cphi; sph = mo.sphi;
+                                L.ptot = mo.ptot; L.pb = mo.pb; L.pperp = mo.pperp; L.gam_pf = mo.gam_pf; L.gd = gd;
+                                L.gr = mo.pperp * P.c * gd;
+                                grt = mo.ptot * P.c * gd;
+                                L.grt = grt;
+                                const double inv_ptot = 1 / mo.ptot, inv_gm = 1 / (mo.gam_pf * P.m);
+                                L.inv_ptot = inv_ptot; L.inv_gm = inv_gm;
+                                mu = mo.pb * inv_ptot; sn = mo.pperp * inv_ptot;
+                                vgm = mo.ptot * inv_gm;
+                                gper = (ELECTRON && mo.ptot < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * gd : TWO_PI * mo.gam_pf * P.mc * gd;
+                                // the boosted momentum may now exceed a cut-off: the pre-test of the next pass parks the lane
+                                st = (st & ~(ST_MUSN | ST_GTPMAX | ST_GTPCUT)) | ST_PHI | (mo.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) |
+                                     (mo.ptot > P.pcut ? ST_GTPCUT : 0u);
                             }
                         }
                     }
                 }
                 MCS_SC(c_fast_iter++;)
-                const unsigned active = __ballot_sync(FULL, ip >= 0);
-                const unsigned waiting = __ballot_sync(FULL, (ip >= 0 && parked) || (ip < 0 && !queue_empty));
-                const int n_act = __popc(active), n_wait = __popc(waiting);
-                if (n_wait > 0 && n_wait >= min(MCS_PARK_T, (3 * n_act + 3) >> 2)) break;
-                if (n_act == 0) break;
+                const int n_wait = __popc(__ballot_sync(FULL, live && (st & ST_PARKED)));
+                if (n_wait > 0 && n_wait >= park_t) break;
 #if MCS_WAIT_DEBT > 0
                 // few lanes waiting for a long time cost as much as many lanes waiting briefly: also leave once the
                 // waiting lanes have idled MCS_WAIT_DEBT lane-iterations in total (short trajectories: many refills)
@@ -1339,50 +1552,57 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 if (wait_debt >= MCS_WAIT_DEBT) break;
 #endif
             }
-            if (need_psp) parked = true;  // left the loop with a boost pending: the general pass does the zone change
-        } else {
-            parked = true;
+            // ---- back to the record ----
+            if (live) {
+                L.x = x; L.acct = acct; L.prp_x = prp_x; L.t_step = t_step; L.gper = gper;
+                if (st & (ST_RAN | ST_PHI)) {  // the phase as an angle in [0, 2 pi), as Base.mod2pi leaves it
+                    double a = atan2(sph, cph);
+                    if (a < 0.0) a += TWO_PI;
+                    L.phi = a;
+                }
+                if (st & ST_MUSN) { L.pb = L.ptot * mu; L.pperp = L.ptot * sn; }
+                if (st & ST_RAN) L.i_return = 2;
+                L.helix = helix;
+                L.i_grid = (int)(gpack & 0xffffu); L.i_grid_old = (int)(gpack >> 16);
+                if (iz != L.iz) {  // the general pass expects the constants of the zone in effect
+                    L.iz = iz;
+                    L.ux = P.ux[iz]; L.gsf = P.gsf[iz]; L.gef = P.gef[iz]; L.bsin = P.sinth[iz]; L.bcos = P.costh[iz];
+                    L.gd = zt.gd[iz];
+                }
+                L.xsel = (st & ST_XSEL) ? 1 : 0;
+                L.down = st & ST_DOWN; L.inj = st & ST_INJ; L.x_old_le0 = st & ST_XOLDLE0;
+                L.parked = (st & (ST_PARKED | ST_NEEDPSP)) != 0u;  // a boost still pending: the general pass does the zone change
+                L.rng_n = rng_n; L.rng_s2 = rng_s2; L.rng_s3 = rng_s3;
+            }
+            L.qn = qn;
         }
     }
     __syncwarp();
-    if (qn > 0) process_events(P, wm, 0, qn);
+    if (L.qn > 0) process_events(P, 0, L.qn);
 
-    MCS_SC(count(P, CNT_FAST_LANE, c_fast_lane); count(P, CNT_SLOW_LANE, c_slow_lane);
-           if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_slow_sec); })
+    MCS_SC(count(P, CNT_FAST_LANE, c_fast_lane);
+           if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_sections); })
     // ---- block partials -------------------------------------------------------------------------------
     __syncthreads();
-    const int np = 4 * ng + SC_N;
+    const int np = 3 * ng + SC_N;
     double* part = P.t.block_partials + (size_t)blockIdx.x * (size_t)np;
     for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        if (i >= 3 * ng && i < 4 * ng) {  // crossing counts: integers
-            unsigned long long s = 0;
-            for (int w = 0; w < n_warps; w++) s += reinterpret_cast<unsigned long long*>(warp_mem(smem, w, ng).part)[i];
-            reinterpret_cast<unsigned long long*>(part)[i] = s;
-        } else {
-            double s = 0.0;
-            for (int w = 0; w < n_warps; w++) s += warp_mem(smem, w, ng).part[i];  // fixed warp order
-            part[i] = s;
-        }
+        double s = 0.0;
+        for (int w = 0; w < n_warps; w++) s += warp_mem(w, ng).part[i];  // fixed warp order
+        part[i] = s;
     }
 }
 
 // Sum the per-block partials in block order (run-to-run deterministic) into the ion totals.
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int ng, double* pxx,
-                                       double* pxz, double* efl, unsigned long long* ncross, double* scalars) {
-    const int np = 4 * ng + SC_N;
+                                       double* pxz, double* efl, double* scalars) {
+    const int np = 3 * ng + SC_N;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
-    if (i >= 3 * ng && i < 4 * ng) {
-        unsigned long long s = 0;
-        const unsigned long long* pu = reinterpret_cast<const unsigned long long*>(partials);
-        for (int b = 0; b < n_blocks; b++) s += pu[(size_t)b * np + i];
-        ncross[i - 3 * ng] += s;
-    } else {
-        double s = 0.0;
-        for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * np + i];
-        double* dst = i < ng ? pxx + i : (i < 2 * ng ? pxz + (i - ng) : (i < 3 * ng ? efl + (i - 2 * ng) : scalars + (i - 4 * ng)));
-        *dst += s;
-    }
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; b++) s += partials[(size_t)b * np + i];
+    double* dst = i < ng ? pxx + i : (i < 2 * ng ? pxz + (i - ng) : (i < 3 * ng ? efl + (i - 2 * ng) : scalars + (i - 3 * ng)));
+    *dst += s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1438,6 +1658,13 @@ __global__ void compact_saved_kernel(const uint8_t* __restrict__ l_save, long lo
     int before = 0;
     for (int k = 0; k < w; k++) before += sh[k];
     if (v) saved_idx[offsets[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u))] = i;
+}
+
+// per-pcut exchange record of one rank, filled on the device so that the all-gather needs no host round trip first
+__global__ void pack_counts_kernel(const unsigned long long* __restrict__ counters, unsigned long long saved0, long long n_use,
+                                   long long err, long long* out) {
+    out[0] = (long long)(counters[CNT_FATE0] - saved0);
+    out[1] = n_use; out[2] = err; out[3] = 0;
 }
 
 __global__ void clone_kernel(PopPtrs src, PopPtrs dst, const long long* __restrict__ saved_idx, long long n_out,

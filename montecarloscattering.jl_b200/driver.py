@@ -145,7 +145,8 @@ def reduce_tallies_host(t: abi.Tallies, comm) -> abi.Tallies:
 
 def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = None, comm=None,
                device_comm: bool = False, want_psd: bool = True, want_log: bool = True, profile_update=None,
-               host_pcut_loop: bool = False, shuffle_population: bool = False, generate_in_library: bool = False):
+               host_pcut_loop: bool = False, shuffle_population: bool = False, generate_in_library: bool = False,
+               only_ions=None):
     """loop_itr / loop_ion / loop_pcut of main_loops.jl:52-341.
 
     Returns a list (per iteration) of lists (per ion) of dicts with the per-ion tallies (pure sums),
@@ -165,7 +166,7 @@ def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = No
         per_ion = []
         for i_ion in range(1, run.n_ions + 1):
             sp = run.species[i_ion - 1]
-            if sp.n0 == 0 and inp.skip_zero_density_species:  # SURVEY B-11
+            if (sp.n0 == 0 and inp.skip_zero_density_species) or (only_ions is not None and i_ion not in only_ions):  # SURVEY B-11
                 per_ion.append(None)
                 continue
             engine.set_profile(prof, eps_target, pool.copy())  # energy_recv_pool .= energy_transfer_pool  :164

