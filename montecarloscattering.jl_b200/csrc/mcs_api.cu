@@ -114,6 +114,7 @@ struct McsHandle {
     int* d_block_cnt = nullptr;
     // tallies: one packed FP64 buffer (single all-reduce) + one packed u64 buffer
     double* d_tally = nullptr;
+    long long* d_acc = nullptr;  // exact accumulators (cfg.det_tallies): ACC_D words per cell of d_tally from off_psd on
     size_t n_tally = 0, off_pxx = 0, off_pxz = 0, off_efl = 0, off_psd = 0, off_esc_up = 0, off_esc_dn = 0, off_en_eff = 0,
            off_num_eff = 0, off_wc = 0, off_sc = 0, off_pool = 0, off_sf = 0, off_pf = 0, off_scal = 0, off_thsf = 0, off_thpf = 0,
            off_dndp = 0;
@@ -173,7 +174,7 @@ extern "C" int mcs_destroy(McsHandle* h) {
     for (auto& p : h->pop) pop_free(p);
     cudaFree(h->d_l_save); cudaFree(h->d_fate); cudaFree(h->d_helix); cudaFree(h->d_retro); cudaFree(h->d_draws);
     cudaFree(h->d_saved_idx); cudaFree(h->d_block_off); cudaFree(h->d_total); cudaFree(h->d_block_cnt);
-    cudaFree(h->d_tally); cudaFree(h->d_u64); cudaFree(h->d_tg); cudaFree(h->d_tpx); cudaFree(h->d_tpt); cudaFree(h->d_tw);
+    cudaFree(h->d_tally); cudaFree(h->d_acc); cudaFree(h->d_u64); cudaFree(h->d_tg); cudaFree(h->d_tpx); cudaFree(h->d_tpt); cudaFree(h->d_tw);
     cudaFree(h->d_inj); cudaFree(h->d_partials); cudaFree(h->d_replay_u); cudaFree(h->d_replay_off); cudaFree(h->d_trace_slot);
     cudaFree(h->d_trace_recs); cudaFree(h->d_trace_cnt); cudaFree(h->d_gather); cudaFree(h->d_xchg);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -216,6 +217,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     memset(h->pop, 0, sizeof h->pop);
     memset(h->h_counters, 0, sizeof h->h_counters);
     h->cfg = *cfg; h->device = dev;
+    h->cfg.det_tallies = env_int("MCS_DET_TALLIES", cfg->det_tallies);  // tuning aid: 0 = FP64 red path
     h->ng = cfg->n_grid; h->M = cfg->num_psd_mom_bins; h->T = cfg->num_psd_theta_bins;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, dev));
@@ -252,6 +254,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     if (cfg->bin_thermal) { h->off_thsf = take(psd_len(h)); h->off_thpf = take(psd_len(h)); h->off_dndp = take((size_t)(h->M + 2) * ng); }
     h->n_tally = o;
     CUA(cudaMalloc(&h->d_tally, o * 8));
+    if (h->cfg.det_tallies) CUA(cudaMalloc(&h->d_acc, o * ACC_D * 8));
     CUA(cudaMalloc(&h->d_u64, (size_t)(ng + CNT_N) * 8));
     const size_t L = (size_t)(cfg->na_cr > 0 ? cfg->na_cr : 1);
     CUA(cudaMalloc(&h->d_tg, L * 8)); CUA(cudaMalloc(&h->d_tpx, L * 8)); CUA(cudaMalloc(&h->d_tpt, L * 8)); CUA(cudaMalloc(&h->d_tw, L * 8));
@@ -308,6 +311,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     t.spec_sf = b + h->off_sf; t.spec_pf = b + h->off_pf;
     t.therm_sf = cfg->bin_thermal ? b + h->off_thsf : nullptr; t.therm_pf = cfg->bin_thermal ? b + h->off_thpf : nullptr;
     t.dndp_cr = cfg->bin_thermal ? b + h->off_dndp : nullptr;
+    t.acc = h->d_acc; t.tally_base = h->d_tally;
     t.counters = h->d_u64 + ng;
     t.ncross = h->d_u64;
     t.tg = h->d_tg; t.tpx = h->d_tpx; t.tpt = h->d_tpt; t.tw = h->d_tw; t.na_cr = cfg->na_cr;
@@ -410,6 +414,7 @@ extern "C" int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const 
     h->n_use = n; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     // clear_psd! (ion_init.jl:1-16) and every other per-ion sum
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
+    if (h->d_acc) CU(cudaMemsetAsync(h->d_acc, 0, h->n_tally * ACC_D * 8, h->stream));
     CU(cudaMemsetAsync(h->d_u64, 0, (size_t)(h->ng + CNT_N) * 8, h->stream));
     memset(h->h_counters, 0, sizeof h->h_counters);
     CU(cudaEventRecord(h->ev2, h->stream));
@@ -454,6 +459,7 @@ extern "C" int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_io
     h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->split_timed = false;
     h->n_use = n_local; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
+    if (h->d_acc) CU(cudaMemsetAsync(h->d_acc, 0, h->n_tally * ACC_D * 8, h->stream));
     CU(cudaMemsetAsync(h->d_u64, 0, (size_t)(h->ng + CNT_N) * 8, h->stream));
     memset(h->h_counters, 0, sizeof h->h_counters);
     CU(cudaEventRecord(h->ev2, h->stream));
@@ -540,8 +546,11 @@ static int launch_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_pr
         int blocks = (int)(want < h->max_blocks ? want : h->max_blocks);
         const size_t smem = block_smem_bytes(h->ng, h->block / 32);
         const bool electron = h->sp.aa < 1;
-        void (*kern)(const DevParams) = debug ? (electron ? transport_kernel<true, true> : transport_kernel<true, false>)
-                                              : (electron ? transport_kernel<false, true> : transport_kernel<false, false>);
+        const bool obl = P.oblique != 0;  // only the fast loop reads it: the debug build has none
+        void (*kern)(const DevParams) =
+            debug ? (electron ? transport_kernel<true, true, false> : transport_kernel<true, false, false>)
+                  : (electron ? (obl ? transport_kernel<false, true, true> : transport_kernel<false, true, false>)
+                              : (obl ? transport_kernel<false, false, true> : transport_kernel<false, false, false>));
         // per function and per device, not per handle: set for THIS launch (another handle may have a smaller grid)
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -812,6 +821,9 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
         h->reduced = true;  // a second call returns the same sums; further pcuts need mcs_begin_ion
         CU(cudaEventRecord(h->ev2, h->stream));
         NC(g_nccl.AllReduce(h->d_tally, h->d_tally, h->n_tally, ncclFloat64, ncclSum, h->comm, h->stream));
+        if (h->d_acc)  // the exact accumulators: integer sum, hence the same words on any number of ranks
+            NC(g_nccl.AllReduce(h->d_acc + h->off_psd * ACC_D, h->d_acc + h->off_psd * ACC_D, (h->n_tally - h->off_psd) * ACC_D, ncclInt64,
+                                ncclSum, h->comm, h->stream));
         NC(g_nccl.AllReduce(h->d_u64, h->d_u64, (size_t)(h->ng + CNT_N), ncclUint64, ncclSum, h->comm, h->stream));
         CU(cudaEventRecord(h->ev3, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -824,6 +836,15 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     CU(cudaEventRecord(h->ev2, h->stream));
     const size_t ng = (size_t)h->ng;
     double* b = h->d_tally;
+    if (h->d_acc) {  // exact accumulators -> FP64 cells (everything but the flux arrays and the scalars)
+        const size_t r0[2] = {h->off_psd, h->off_thsf}, r1[2] = {h->off_scal, h->off_dndp};
+        for (int k = 0; k < (h->cfg.bin_thermal ? 2 : 1); k++) {
+            const size_t n = r1[k] - r0[k];
+            fold_accumulators_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_acc, r0[k], r1[k], h->d_tally);
+            CU(cudaGetLastError());
+            h->tm.other_launches++;
+        }
+    }
     if (h->cfg.bin_thermal) {
         const int M2 = h->M + 2, T2 = h->T + 2;
         sum_angle_kernel<<<(M2 * h->ng + 255) / 256, 256, 0, h->stream>>>(b + h->off_psd, M2, T2, h->ng, b + h->off_dndp);

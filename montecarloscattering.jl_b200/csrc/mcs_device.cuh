@@ -30,7 +30,7 @@
 #define MCS_BLOCK 256
 #endif
 #ifndef MCS_MIN_BLOCKS
-#define MCS_MIN_BLOCKS 3
+#define MCS_MIN_BLOCKS 2
 #endif
 #ifndef MCS_PARK_T
 #define MCS_PARK_T 16     // lanes that must be waiting (parked or refillable) before the warp leaves the fast loop
@@ -46,6 +46,13 @@
 #endif
 #ifndef MCS_FAST_MAX
 #define MCS_FAST_MAX 256  // safety bound on consecutive fast passes
+#endif
+
+// Out-of-line cold functions follow the call ABI; MCS_INLINE_COLD folds them into their callers instead (tuning aid).
+#ifdef MCS_INLINE_COLD
+#define MCS_COLD __forceinline__
+#else
+#define MCS_COLD __noinline__
 #endif
 
 namespace mcs {
@@ -108,6 +115,8 @@ struct TallyPtrs {
     long long* tg;          // thermal-crossing log
     double *tpx, *tpt, *tw;
     long long na_cr;
+    long long* acc;              // exact fixed-point accumulators, ACC_D digits per cell of the packed tally buffer, or null
+    const double* tally_base;    // first cell of the packed FP64 tally buffer (cell index = pointer - tally_base)
     unsigned long long* ncross;  // [n_grid] thermal crossings per zone (integer adds: any order gives the same bits)
     double* block_partials; // [gridDim.x][3*n_grid + SC_N]: pxx | pxz | efl | scalars
 };
@@ -207,6 +216,51 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 }
 __device__ __forceinline__ void count(const DevParams& P, int which, unsigned long long v = 1ull) {
     red_add_u64(&P.t.counters[which], v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact accumulation of the large histograms (McsConfig.det_tallies).  A cell is ACC_D signed 64-bit words, word k holding
+// the multiples of 2^(ACC_ELO + 32 k): a contribution m * 2^e (m its 53-bit significand) is cut at the word boundaries into
+// at most three pieces of < 2^32 and each piece is ADDED to its word with an integer atomic.  Integer adds commute and the
+// words have 31 bits of headroom (2^31 contributions per cell before a carry could be lost), so the words — and the double
+// they are folded into at the end of the ion — do not depend on the order of the adds: bitwise identical run to run, for
+// any schedule and any number of GPUs (the per-rank words are summed with an integer all-reduce).  The window is fixed:
+// values in [2^-157, 2^98) keep all 53 bits, smaller ones lose their low bits below 2^-210, anything else is counted as an
+// error.  (Weights here are ~1e-6 at injection and shrink by up to ~1e-20 in a deep pcut ladder; 1/v >= 3e-11.)
+constexpr int ACC_D = 10;
+constexpr int ACC_ELO = -210;
+__device__ __forceinline__ int acc_add(const DevParams& P, size_t cell, double v);
+// one tally update: exact accumulator when configured, else an FP64 red into the cell itself
+__device__ __forceinline__ int tally_add(const DevParams& P, double* cell, double v) {
+    if (P.t.acc != nullptr) return acc_add(P, (size_t)(cell - P.t.tally_base), v);
+    red_add_f64(cell, v);
+    return 1;
+}
+__device__ __forceinline__ int acc_add(const DevParams& P, size_t cell, double v) {
+    const long long bits = __double_as_longlong(v);
+    const int ex = (int)((bits >> 52) & 0x7ff);
+    unsigned long long m = (unsigned long long)bits & 0x000fffffffffffffull;
+    if (ex == 0 && m == 0) return 0;
+    if (ex == 0x7ff) { count(P, CNT_ERR); return 0; }  // NaN / inf: the reference would have thrown long before
+    int e = (ex ? ex : 1) - 1075;
+    if (ex) m |= 0x0010000000000000ull;
+    int s = e - ACC_ELO;
+    if (s < 0) {  // below the window: keep what reaches it
+        if (s <= -53) return 0;
+        m >>= -s;
+        s = 0;
+    }
+    const int k0 = s >> 5, r = s & 31;
+    if (k0 + 2 >= ACC_D) { count(P, CNT_ERR); return 0; }  // beyond 2^98
+    const unsigned long long lo64 = m << r, hi64 = r ? (m >> (64 - r)) : 0ull;
+    unsigned long long d0 = lo64 & 0xffffffffull, d1 = lo64 >> 32, d2 = hi64;
+    if (bits < 0) { d0 = 0ull - d0; d1 = 0ull - d1; d2 = 0ull - d2; }
+    unsigned long long* c = reinterpret_cast<unsigned long long*>(P.t.acc) + cell * ACC_D + k0;
+    int n = 0;
+    if (d0) { red_add_u64(c, d0); n++; }
+    if (d1) { red_add_u64(c + 1, d1); n++; }
+    if (d2) { red_add_u64(c + 2, d2); n++; }
+    return n;
 }
 
 // RNG: Philox4x32-10, counter = (block, i_prt, i_pcut | i_ion<<16, i_iter), key = seed. Replaces the
@@ -434,7 +488,7 @@ __device__ __noinline__ Mom transform_p_PSP(const DevParams& P, int io, int in, 
 // sincos(phi + pi/2) is (cos phi, -sin phi), and its new phase atan(ny, d) - pi/2 has cosine ny / h and sine -d / h with
 // h = hypot(ny, d): no trigonometric call at all.
 struct MomCS { double ptot, pb, pperp, gam_pf, cphi, sphi; };
-__device__ __noinline__ MomCS transform_p_PSP_cs(const DevParams& P, int io, int in, MomCS mi) {
+__device__ MCS_COLD MomCS transform_p_PSP_cs(const DevParams& P, int io, int in, MomCS mi) {
     const double pb = mi.pb, pperp = mi.pperp, gam_pf = mi.gam_pf;
     const double ux_o = P.ux[io], uz_o = P.uz[io], gsf_o = P.gsf[io], bcos_o = P.costh[io], bsin_o = P.sinth[io];
     const double ux = P.ux[in], uz = P.uz[in], gsf = P.gsf[in], bcos = P.costh[in], bsin = P.sinth[in];
@@ -484,10 +538,10 @@ __device__ __forceinline__ double radiation_loss(const DevParams& P, double B2, 
 
 // cuts.jl:149-162
 __device__ __noinline__ void tcut_track(const DevParams& P, int tcut_curr, double weight, double ptot) {
-    count(P, CNT_RED, 2ull);
-    red_add_f64(&P.t.w_coupled[tcut_curr - 1], weight);
+    int n = tally_add(P, &P.t.w_coupled[tcut_curr - 1], weight);
     int ip = psd_bin_momentum(P, ptot);
-    red_add_f64(&P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
+    n += tally_add(P, &P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
+    count(P, CNT_RED, (unsigned long long)n);
 }
 
 // particle_loop.jl:652-723
@@ -508,9 +562,10 @@ __device__ __noinline__ Mom do_energy_transfer(const DevParams& P, int i_grid, i
         int n_split = 0;
         for (int i = i_start + 1; i <= i_stop; i++) n_split += P.eps_target[i - 1] > 0;
         double inc = (gam_i - gam_f) * E0 * weight / n_split;
-        count(P, CNT_RED, (unsigned long long)n_split);
+        int n = 0;
         for (int i = i_start + 1; i <= i_stop; i++)
-            if (P.eps_target[i - 1] > 0) red_add_f64(&P.t.pool[i - 1], inc);
+            if (P.eps_target[i - 1] > 0) n += tally_add(P, &P.t.pool[i - 1], inc);
+        count(P, CNT_RED, (unsigned long long)n);
         scale = true;
     } else if (rmax > 0) {
         double sum = 0.0;
@@ -593,21 +648,23 @@ __device__ __forceinline__ bool retro_time(const DevParams& P, Rng& rng, double&
 
 // what get_dNdp_2D (particle_counter.jl:426-445) and thermo_calcs (thermo_calcs.jl:133-164) build from the
 // crossing log, accumulated on the fly so the log can stay small.  Out of line: only runs with cfg.bin_thermal.
-__device__ __noinline__ void bin_thermal_crossing(const DevParams& P, int lo, int hi, double sx, double ptot_sk, double gam_sk,
-                                                  double ux, double weight) {
+__device__ __noinline__ int bin_thermal_crossing(const DevParams& P, int lo, int hi, double sx, double ptot_sk, double gam_sk,
+                                                 double ux, double weight) {
+    int n_at = 0;
     const double w = weight * (ptot_sk > fabs(sx * SPIKE_AWAY) ? fabs(SPIKE_AWAY / ux) : fabs(gam_sk * P.aa * P.mp / sx));
     const size_t sT = (size_t)(P.T + 2), sM = (size_t)(P.M + 2);
     const int k = psd_bin_momentum(P, ptot_sk), jt = psd_bin_angle(P, sx, ptot_sk);
     const double E0 = P.m * (P.c * P.c), etot = hypot(ptot_sk * P.c, E0);
     for (int i = lo; i <= hi; i++) {
-        red_add_f64(&P.t.therm_sf[(size_t)jt + sT * ((size_t)k + sM * (size_t)(i - 1))], w);
+        n_at += tally_add(P, &P.t.therm_sf[(size_t)jt + sT * ((size_t)k + sM * (size_t)(i - 1))], w);
         const double g = P.gsf[i], b = P.ux[i] / P.c;
         double pxX = g * (sx - b * etot / P.c);
         const double ptX = sqrt((ptot_sk * ptot_sk - sx * sx) + pxX * pxX);
         if (fabs(pxX) > ptX) pxX = copysign(ptX, pxX);
         const int kX = psd_bin_momentum(P, ptX), jX = psd_bin_angle(P, pxX, ptX);
-        red_add_f64(&P.t.therm_pf[(size_t)jX + sT * ((size_t)kX + sM * (size_t)(i - 1))], w);
+        n_at += tally_add(P, &P.t.therm_pf[(size_t)jX + sT * ((size_t)kX + sM * (size_t)(i - 1))], w);
     }
+    return n_at;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -616,7 +673,7 @@ __device__ __noinline__ void bin_thermal_crossing(const DevParams& P, int lo, in
 //                     upstream-FEB scalars);
 //   finish event   -> particle_finish.jl:46-107 and the downstream sums of particle_loop.jl:478-495.
 // The n_grid-sized tallies and the scalars go to this warp's shared partials with plain adds in event order.
-__device__ __noinline__ void process_events(const DevParams& P, int base, int n_ev) {
+__device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) {
     const int lane = threadIdx.x & 31, ng = P.n_grid;
     const WarpMem wm = warp_mem(threadIdx.x >> 5, ng);
     const bool act = lane < n_ev;
@@ -658,10 +715,9 @@ __device__ __noinline__ void process_events(const DevParams& P, int base, int n_
             int ipt = psd_bin_momentum(P, ptot_sk), ipf = psd_bin_momentum(P, ptot);
             for (int i = 0; i < P.n_xspec; i++)
                 if (xmask & (1u << i)) {
-                    n_red += 2;
-                    red_add_f64(&P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
+                    n_red += tally_add(P, &P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
                     double F = fabs(pb / sx) * (gam_sk / gam_pf);
-                    red_add_f64(&P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
+                    n_red += tally_add(P, &P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
                 }
         }
         const double sign_fac = up ? -1.0 : 1.0;
@@ -676,8 +732,7 @@ __device__ __noinline__ void process_events(const DevParams& P, int base, int n_
                 int ipt = psd_bin_momentum(P, ptot_sk), jth = psd_bin_angle(P, sx, ptot_sk);
                 const size_t stride = (size_t)(P.M + 2) * (size_t)(P.T + 2);
                 double* cell = P.t.psd + (size_t)ipt + (size_t)(P.M + 2) * (size_t)jth + stride * (size_t)(lo - 1);
-                for (int i = lo; i <= hi; i++, cell += stride) red_add_f64(cell, w);
-                n_red += hi - lo + 1;
+                for (int i = lo; i <= hi; i++, cell += stride) n_red += tally_add(P, cell, w);
             } else {
                 thermal = true;
                 n_red += hi - lo + 1;  // crossing counts
@@ -713,7 +768,7 @@ __device__ __noinline__ void process_events(const DevParams& P, int base, int n_
                 if (over) count(P, CNT_LOG_OVER, (unsigned long long)over);
             }
         }
-        if (P.t.therm_sf != nullptr && nrec > 0) { bin_thermal_crossing(P, lo, hi, sx, ptot_sk, gam_sk, ux, weight); n_red += 2 * nrec; }
+        if (P.t.therm_sf != nullptr && nrec > 0) n_red += bin_thermal_crossing(P, lo, hi, sx, ptot_sk, gam_sk, ux, weight);
     }
     if (is_fin) {
         const int reason = (fl >> EV_REASON_SHIFT) & 7;
@@ -723,19 +778,18 @@ __device__ __noinline__ void process_events(const DevParams& P, int base, int n_
             double wf;
             if (ptot_sk > fabs(SPIKE_AWAY * sx)) wf = gam_sk * P.m * SPIKE_AWAY / ptot_sk;
             else wf = gam_sk * (P.m / fabs(sx));
-            n_red += reason == 1 ? 1 : 3;
             if (reason == 1) {
-                red_add_f64(&P.t.esc_dn[ip + E1 * jt], weight * wf);
+                n_red += tally_add(P, &P.t.esc_dn[ip + E1 * jt], weight * wf);
             } else {
                 sc[SC_ESC_FLUX] = weight;
-                red_add_f64(&P.t.esc_up[ip + E1 * jt], weight * wf);
+                n_red += tally_add(P, &P.t.esc_up[ip + E1 * jt], weight * wf);
                 bool rel = (gam_sk - 1) >= P.E_rel_pt;  // F-8
                 double Ek = rel ? (gam_sk - 1) * E0 : ptot_sk * ptot_sk / (2 * P.m);
                 double en_add = Ek * weight;
                 sc[SC_PX_ESC_FEB] = fabs(sx) * weight;
                 sc[SC_EN_ESC_FEB] = en_add;
-                red_add_f64(&P.t.esc_en_eff[ip], en_add);
-                red_add_f64(&P.t.esc_num_eff[ip], weight);
+                n_red += tally_add(P, &P.t.esc_en_eff[ip], en_add);
+                n_red += tally_add(P, &P.t.esc_num_eff[ip], weight);
             }
         }
         if (fl & EV_SUMP) {  // particle_loop.jl:478-486
@@ -745,8 +799,27 @@ __device__ __noinline__ void process_events(const DevParams& P, int base, int n_
             sc[SC_SUMKE] = (gam_pf - 1) * P.m * (P.c * P.c) * weight * P.n0;
         }
     }
-    // ---- ordered accumulation into the warp's partials: events in queue order, lanes spread over the zones ----
-    unsigned todo = __ballot_sync(FULL, is_cross && lo <= hi);
+    // ---- ordered accumulation into the warp's partials --------------------------------------------------------------
+    // Nearly every crossing covers ONE zone.  Those are added by their own lanes, all zones in parallel: lanes that hit the
+    // same zone take turns in lane (= queue) order, so the order of the adds into any cell is fixed.  The few events that
+    // span several zones follow, one after the other, with the lanes spread over the zones.
+    {
+        const bool single = is_cross && lo == hi;
+        const unsigned peers = __match_any_sync(FULL, single ? lo : -1 - lane);
+        const int turn = __popc(peers & ((1u << lane) - 1u));
+        int n_turns = single ? __popc(peers) : 0;
+        for (int o = 16; o > 0; o >>= 1) n_turns = max(n_turns, __shfl_xor_sync(FULL, n_turns, o));
+        for (int r = 0; r < n_turns; r++) {
+            if (single && turn == r) {
+                wm.part[lo - 1] += f_pxx;
+                wm.part[ng + lo - 1] += f_pxz;
+                wm.part[2 * ng + lo - 1] += f_en;
+            }
+            __syncwarp();
+        }
+        if (single && thermal) red_add_u64(&P.t.ncross[lo - 1], 1ull);  // integer adds: any order
+    }
+    unsigned todo = __ballot_sync(FULL, is_cross && lo < hi);
     while (todo) {
         const int e = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -1259,7 +1332,9 @@ enum : uint32_t {
     ST_RAN = 256u,   // at least one fast pass committed in this residency (i_return = 2)
     ST_MUSN = 512u,  // mu / sn are newer than the record's pb / pperp
     ST_PHI = 1024u,  // the phase registers are newer than the record's angle (a boost without a committed pass after it)
+    ST_ETF = 2048u,  // energy transfer is due before the next pass (particle_loop.jl:235): general pass
 };
+constexpr double COS_AT_LIMIT = 1.4901161193847656e-08;  // sqrt(1 - prevfloat(1.0)^2): cosine of the phase change at the clamp
 
 // sin and cos of the scattering azimuth phi_s = 2 pi u - pi (scattering.jl:71) for u = w / 2^53, w the 53-bit random
 // integer (hi:lo >> 11): the top 8 bits of w pick a table entry {sin A_k, cos A_k}, A_k = -pi + 2 pi (k + 1/2) / 256, the
@@ -1295,8 +1370,13 @@ __device__ __forceinline__ double mod2pi_bf(double v, bool& ok) {
 
 // ---------------------------------------------------------------------------------------------
 // The transport kernel.
-template <bool DEBUG, bool ELECTRON>
-__global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(const __grid_constant__ DevParams P) {
+#ifdef MCS_MAXNREG
+#define MCS_KERNEL_BOUNDS __maxnreg__(MCS_MAXNREG)
+#else
+#define MCS_KERNEL_BOUNDS __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS)
+#endif
+template <bool DEBUG, bool ELECTRON, bool OBLIQUE>
+__global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char mcs_smem[];
     const int ng = P.n_grid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -1362,8 +1442,17 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             uint32_t gpack = (uint32_t)L.i_grid | ((uint32_t)L.i_grid_old << 16);
             uint32_t rng_n = L.rng_n, rng_s2 = L.rng_s2, rng_s3 = L.rng_s3;
             const uint32_t rng_c1 = L.rng_c1;
+            // status word; ST_PRE = "the general pass must see this particle before its next pass" for the reasons that only
+            // change at a boost, a shock crossing or a zone change (momentum above a cut-off, pending energy transfer)
             uint32_t st = (L.down ? ST_DOWN : 0u) | (L.inj ? ST_INJ : 0u) | (L.x_old_le0 ? ST_XOLDLE0 : 0u) | (L.xsel ? ST_XSEL : 0u) |
                           (L.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) | (L.ptot > P.pcut ? ST_GTPCUT : 0u);
+            if (P.energy_transfer_frac > 0 && !L.inj && L.x_old_le0 && L.i_grid_old != L.i_grid) st |= ST_ETF;
+            // The Philox block of the NEXT pass is produced during the current one (integer pipe, independent of the
+            // FP64 chain): q* = block (rng_n + odd) / 2 of this particle's stream.
+#ifdef MCS_PREFETCH
+            uint32_t q0, q1, q2, q3;
+            philox4x32_10_rk((rng_n + (rng_n & 1u)) >> 1, rng_c1, P.ctr2, P.ctr3, P.rk, q0, q1, q2, q3);
+#endif
             const int n_act = __popc(__ballot_sync(FULL, live));
             const int park_t = min(MCS_PARK_T, (3 * n_act + 3) >> 2);
             int psp_debt = 0, wait_debt = 0;
@@ -1372,13 +1461,10 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                 int ev_old = 0;     // its zone before the move
                 if (live && !(st & (ST_PARKED | ST_NEEDPSP))) {
                     const int ig = (int)(gpack & 0xffffu);
-                    // what the general pass must see before this pass: helix cap, a momentum above a cut-off, pending energy
-                    // transfer, age
-                    uint32_t park = (helix >= P.helix_cap) ? 1u : 0u;
-                    park |= st & ST_GTPMAX;
-                    park |= ((st & (ST_DOWN | ST_GTPCUT)) == (ST_DOWN | ST_GTPCUT)) ? 1u : 0u;
-                    if (P.energy_transfer_frac > 0) park |= ((st & (ST_INJ | ST_XOLDLE0)) == ST_XOLDLE0 && (int)(gpack >> 16) != ig) ? 1u : 0u;
-                    if (P.age_max > 0) park |= (acct > P.age_max) ? 1u : 0u;
+                    // what the general pass must see before this pass: helix cap, a momentum above a cut-off (saved when
+                    // downstream), pending energy transfer, age
+                    bool park = (helix >= P.helix_cap) || (st & (ST_GTPMAX | ST_ETF)) || ((st & (ST_DOWN | ST_GTPCUT)) == (ST_DOWN | ST_GTPCUT));
+                    if (P.age_max > 0) park = park || acct > P.age_max;
                     if (ig != iz && !park) {
                         // Code Block 3 zone change (particle_loop.jl:186-228): without a change of flow speed only the
                         // zone's constants change; with one, the momentum must be boosted (batched below)
@@ -1390,115 +1476,127 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
                             iz = ig;
                         }
                     }
-                    if (!(st & ST_NEEDPSP)) {
+                    if (!(st & ST_NEEDPSP) && !park) {
+                        // scattering.jl:29-101, same kick as the general pass.  Differences in form only: the azimuth's
+                        // sine and cosine come from the table; sqrt(w) is w * rsqrt(w) and the three of them overlap
+                        // (sin_new and the pair (sv, cv) = (sin, cos) of the phase change asin(sv) share one reciprocal
+                        // square root of sn2); the phase change is applied as a rotation.
+                        const bool xs_n = x > grt;                                   // particle_loop.jl:385, decided first
+                        const int xi = xs_n ? 1 : 0;
+                        const double t_n = gper * P.inv_xn[xi];
+                        const double cd = P.cdphi[xi], sd = P.sdphi[xi];
+                        const double omc = P.omc[(st & ST_XSEL) ? 1 : 0];
+                        const uint32_t odd = rng_n & 1u;
+#ifndef MCS_PREFETCH
+                        uint32_t q0, q1, q2, q3;
+                        philox4x32_10_rk((rng_n + odd) >> 1, rng_c1, P.ctr2, P.ctr3, P.rk, q0, q1, q2, q3);
+#endif
+                        const double u1 = odd ? u53(rng_s3, rng_s2) : u53(q1, q0);
+                        double sps, cps;
+                        az_sincos(zt.az, odd ? q1 : q3, odd ? q0 : q2, sps, cps);
+                        const uint32_t l2 = q2, l3 = q3;                             // left over for an odd-aligned successor
+#ifdef MCS_PREFETCH
+                        philox4x32_10_rk(((rng_n + odd) >> 1) + 1u, rng_c1, P.ctr2, P.ctr3, P.rk, q0, q1, q2, q3);
+#endif
+                        const double cos_d = 1 - u1 * omc;
+                        const double sd2 = 1 - cos_d * cos_d;
+                        const double sin_d = sd2 * rsqrt_nr(sd2);                    // NaN for sd2 == 0: parks below
+                        const double cos_new = mu * cos_d + sn * sin_d * cps;
+                        const double sn2 = 1 - cos_new * cos_new;
+                        const double a = sps * sin_d;
+                        const double r = rsqrt_nr(sn2);
+                        const double w2 = sn2 - a * a;
+                        const double r2 = rsqrt_nr(w2);
+                        const double sin_new = sn2 * r;
+                        double sv = a * r;
+                        double cv = (w2 * r2) * r;                                   // sqrt(1 - sv^2) = sqrt(sn2 - a^2) / sin_new
+                        if (fabs(sv) > SIN_UPPER_LIMIT) sv = copysign(SIN_UPPER_LIMIT, sv);
+                        cv = cv > COS_AT_LIMIT ? cv : COS_AT_LIMIT;                  // also catches the NaN of w2 <= 0 at the clamp
+                        const double c1 = cph * cv - sph * sv, s1 = sph * cv + cph * sv;
+                        // Code Block 2 move
+                        const double cph_n = c1 * cd - s1 * sd, sph_n = s1 * cd + c1 * sd;
                         const double2 za = zt.a[iz], zb = zt.b[iz], zc = zt.c[iz];  // {ux, gsf} {gef, cos th} {xg[iz], xg[iz+1]}
+                        const double x_move = (cos_new * vgm) * t_n;
+                        double gyr = 0.0;
+                        if (OBLIQUE) {
+                            const double bsin = P.sinth[iz];
+                            if (bsin != 0.0) gyr = L.gr * bsin * (cph_n - c1);
+                        }
+                        const double x_n = x + za.y * (x_move * zb.y - gyr + za.x * t_n);
                         double acct_n = acct;
                         if (st & ST_DOWN) {
                             acct_n = acct + t_step * zb.x;
-                            if (flags & F_TCUTS) park |= (L.tcut <= P.n_tcuts && acct_n >= P.tcuts[L.tcut - 1]) ? 1u : 0u;
+                            if (flags & F_TCUTS) park = L.tcut <= P.n_tcuts && acct_n >= P.tcuts[L.tcut - 1];
                         }
-                        if (!park) {
-                            // scattering.jl:29-101: same kick as the general pass; the azimuth's sine and cosine come
-                            // from the table, the phase change asin(s) is applied as the rotation (sqrt(1 - s^2), s)
-                            const double omc = P.omc[(st & ST_XSEL) ? 1 : 0];
-                            // one Philox block per pass whether or not the stream is block-aligned
-                            const uint32_t odd = rng_n & 1u;
-                            uint32_t o0, o1, o2, o3;
-                            philox4x32_10_rk((rng_n + odd) >> 1, rng_c1, P.ctr2, P.ctr3, P.rk, o0, o1, o2, o3);
-                            const double u1 = odd ? u53(rng_s3, rng_s2) : u53(o1, o0);
-                            double sps, cps;
-                            az_sincos(zt.az, odd ? o1 : o3, odd ? o0 : o2, sps, cps);
-                            const double cos_d = 1 - u1 * omc;
-                            const double sd2 = 1 - cos_d * cos_d;
-                            // sqrt_nr/div_nr: NaN for sd2 == 0 or sn2 <= 0 -> sn2 turns NaN -> the lane parks below
-                            const double sin_d = sqrt_nr(sd2);
-                            const double cos_new = mu * cos_d + sn * sin_d * cps;
-                            const double sn2 = 1 - cos_new * cos_new;
-                            const double sin_new = sqrt_nr(sn2);
-                            double sv = div_nr(sps * sin_d, sin_new);
-                            if (fabs(sv) > SIN_UPPER_LIMIT) sv = copysign(SIN_UPPER_LIMIT, sv);
-                            const double cv = sqrt_nr(1 - sv * sv);  // cos(asin(sv)) >= 0
-                            const double c1 = cph * cv - sph * sv, s1 = sph * cv + cph * sv;
-                            // Code Block 2 move
-                            const bool xs_n = x > grt;
-                            const int xi = xs_n ? 1 : 0;
-                            const double t_n = gper * P.inv_xn[xi];
-                            const double cd = P.cdphi[xi], sd = P.sdphi[xi];
-                            const double cph_n = c1 * cd - s1 * sd, sph_n = s1 * cd + c1 * sd;
-                            const double x_move = (cos_new * vgm) * t_n;
-                            double gyr = 0.0;
-                            if (P.oblique) {
-                                const double bsin = P.sinth[iz];
-                                if (bsin != 0.0) gyr = L.gr * bsin * (cph_n - c1);
+                        // Is this a plain pass?  Same zone, and inside the grid or between its end and the PRP.
+                        const bool dn = x_n > x;
+                        const bool same = dn ? (zc.y > x_n) : (zc.x <= x_n);
+                        bool rare = !same | !(sn2 > 0.0) | park | ((x_n >= P.x_grid_stop) & ((x < P.x_grid_stop) | (x_n >= prp_x) | ELECTRON));
+                        if (st & ST_INJ) rare |= x_n < P.feb_up;
+                        if (P.feb_dn > 0) rare |= x_n > P.feb_dn;
+                        if (reflect_cfg) rare |= (x_n <= 0) & (x > 0);
+                        int ig_new = iz;
+                        double prp_n = prp_x;
+                        uint32_t st_n = st;
+                        bool go = true;
+                        if (rare) {
+                            // anything the general pass would have to act on after the move -> nothing is committed
+                            bool pk = park | !(sn2 > 0.0) | !(x_n == x_n) | (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) |
+                                      (P.feb_dn > 0 && x_n > P.feb_dn);
+                            const bool cross_down = x < 0 && x_n >= 0;
+                            if (cross_down) {  // particle_loop.jl:413-429: arrival downstream, make the region long enough
+                                const double Ld = P.eta_mfp / 3 * grt * L.ptot / (P.m * L.gam_pf * P.u2);
+                                prp_n = fmax(prp_x, Ld);
                             }
-                            const double x_n = x + za.y * (x_move * zb.y - gyr + za.x * t_n);
-                            // Is this a plain pass?  Same zone, and inside the grid or between its end and the PRP.
-                            const bool dn = x_n > x;
-                            const bool same = dn ? (zc.y > x_n) : (zc.x <= x_n);
-                            bool rare = !same | !(sn2 > 0.0) | !(cph_n == cph_n) |
-                                        ((x_n >= P.x_grid_stop) & ((x < P.x_grid_stop) | (x_n >= prp_x) | ELECTRON));
-                            if (st & ST_INJ) rare |= x_n < P.feb_up;
-                            if (P.feb_dn > 0) rare |= x_n > P.feb_dn;
-                            if (reflect_cfg) rare |= (x_n <= 0) & (x > 0);
-                            int ig_new = iz;
-                            double prp_n = prp_x;
-                            uint32_t st_n = st;
-                            bool go = true;
-                            if (rare) {
-                                // anything the general pass would have to act on after the move -> nothing is committed
-                                bool pk = !(sn2 > 0.0) | !(cph_n == cph_n) | !(x_n == x_n) |
-                                          (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) | (P.feb_dn > 0 && x_n > P.feb_dn);
-                                const bool cross_down = x < 0 && x_n >= 0;
-                                if (cross_down) {  // particle_loop.jl:413-429: arrival downstream, make the region long enough
-                                    const double Ld = P.eta_mfp / 3 * grt * L.ptot / (P.m * L.gam_pf * P.u2);
-                                    prp_n = fmax(prp_x, Ld);
-                                }
-                                if (x_n > 1.1 * prp_n) {
-                                    // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes beyond 6.91 L_diff
-                                    double v_fac;
-                                    if (ELECTRON && L.ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * zt.gd[iz]) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
-                                    else v_fac = grt * L.ptot / (P.m * L.gam_pf * P.u2);
-                                    pk |= x_n > 6.91 * (P.eta_mfp / 3 * v_fac);
-                                }
-                                if (x_n >= P.x_grid_stop) {
-                                    if (x < P.x_grid_stop) {
-                                        // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP
-                                        const double g2 = L.ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
-                                        prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * L.ptot / (P.aa * P.mp * L.gam_pf * P.u2));
-                                    } else {
-                                        pk |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
-                                    }
-                                }
-                                if (!pk) {
-                                    // zone search (all_flux.jl:65-82) and the crossing event
-                                    if (!same) {
-                                        if (dn) { int k = iz + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig_new = k - 1; }
-                                        else { int k = iz; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig_new = k; }
-                                    }
-                                    if (cross_down) st_n |= ST_DOWN;
-                                    if ((st_n & ST_DOWN) && x_n < 0) st_n |= ST_INJ;  // particle_loop.jl:433-435 (before all_flux)
-                                    const bool below_feb = (st_n & ST_INJ) && x_n < P.feb_up;
-                                    const bool feb_x = below_feb && x >= P.feb_up;
-                                    if (ig_new != iz || (feb_x && ig_new <= P.i_grid_feb))
-                                        fev = EV_VALID | ((st_n & ST_INJ) ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
-                                    if (below_feb) st_n |= ST_PARKED;  // the next pass ends at the upstream FEB: general pass
-                                }
-                                go = !pk;
+                            if (x_n > 1.1 * prp_n) {
+                                // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes beyond 6.91 L_diff
+                                double v_fac;
+                                if (ELECTRON && L.ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * zt.gd[iz]) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
+                                else v_fac = grt * L.ptot / (P.m * L.gam_pf * P.u2);
+                                pk |= x_n > 6.91 * (P.eta_mfp / 3 * v_fac);
                             }
-                            if (go) {
-                                ev_old = iz;
-                                st = (st_n & ~(ST_XOLDLE0 | ST_XSEL)) | (x <= 0.0 ? ST_XOLDLE0 : 0u) | (xs_n ? ST_XSEL : 0u) | ST_RAN | ST_MUSN;
-                                prp_x = prp_n;
-                                helix++; MCS_SC(c_fast_lane++;)
-                                acct = acct_n; t_step = t_n;
-                                mu = cos_new; sn = sin_new; cph = cph_n; sph = sph_n; x = x_n;
-                                gpack = (uint32_t)ig_new | ((uint32_t)iz << 16);
-                                rng_n += 2; rng_s2 = o2; rng_s3 = o3;
-                            } else {
-                                park = 1u;
+                            if (x_n >= P.x_grid_stop) {
+                                if (x < P.x_grid_stop) {
+                                    // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP
+                                    const double g2 = L.ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
+                                    prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * L.ptot / (P.aa * P.mp * L.gam_pf * P.u2));
+                                } else {
+                                    pk |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
+                                }
                             }
+                            if (!pk) {
+                                // zone search (all_flux.jl:65-82) and the crossing event
+                                if (!same) {
+                                    if (dn) { int k = iz + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig_new = k - 1; }
+                                    else { int k = iz; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig_new = k; }
+                                }
+                                if (cross_down) st_n |= ST_DOWN;
+                                if ((st_n & ST_DOWN) && x_n < 0) st_n |= ST_INJ;  // particle_loop.jl:433-435 (before all_flux)
+                                const bool below_feb = (st_n & ST_INJ) && x_n < P.feb_up;
+                                const bool feb_x = below_feb && x >= P.feb_up;
+                                if (ig_new != iz || (feb_x && ig_new <= P.i_grid_feb))
+                                    fev = EV_VALID | ((st_n & ST_INJ) ? EV_INJ : 0u) | (dn ? 0u : EV_UP) | (feb_x ? EV_FEB_UP : 0u);
+                                if (below_feb) st_n |= ST_PARKED;  // the next pass ends at the upstream FEB: general pass
+                                // energy transfer is due at the next pass of a not yet injected particle that changed zone
+                                // coming from x <= 0 (particle_loop.jl:235)
+                                if (P.energy_transfer_frac > 0 && !(st_n & ST_INJ) && x <= 0.0 && ig_new != iz) st_n |= ST_ETF;
+                            }
+                            go = !pk;
                         }
-                        if (park) st |= ST_PARKED;
+                        if (go) {
+                            ev_old = iz;
+                            st = (st_n & ~(ST_XOLDLE0 | ST_XSEL | ST_PHI)) | (x <= 0.0 ? ST_XOLDLE0 : 0u) | (xs_n ? ST_XSEL : 0u) | ST_RAN | ST_MUSN;
+                            prp_x = prp_n;
+                            helix++; MCS_SC(c_fast_lane++;)
+                            acct = acct_n; t_step = t_n;
+                            mu = cos_new; sn = sin_new; cph = cph_n; sph = sph_n; x = x_n;
+                            gpack = (uint32_t)ig_new | ((uint32_t)iz << 16);
+                            rng_n += 2; rng_s2 = l2; rng_s3 = l3;
+                        } else {
+                            st |= ST_PARKED;  // (the prefetched block is stale now; it is rebuilt when the lane re-enters the loop)
+                        }
+                    } else if (park) {
+                        st |= ST_PARKED;
                     }
                 }
                 // converged: queue the crossing events of this pass (state right after the move, as at point A)
@@ -1555,7 +1653,11 @@ __global__ void __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS) transport_kernel(co
             // ---- back to the record ----
             if (live) {
                 L.x = x; L.acct = acct; L.prp_x = prp_x; L.t_step = t_step; L.gper = gper;
-                if (st & (ST_RAN | ST_PHI)) {  // the phase as an angle in [0, 2 pi), as Base.mod2pi leaves it
+                if (st & ST_PHI) {  // last touched by a boost: atan(...) - pi/2 lies in (-3 pi/2, pi/2] (transformers.jl:603-604)
+                    double a = atan2(sph, cph);
+                    if (a > HALF_PI) a -= TWO_PI;
+                    L.phi = a;
+                } else if (st & ST_RAN) {  // last touched by a move: Base.mod2pi leaves it in [0, 2 pi)
                     double a = atan2(sph, cph);
                     if (a < 0.0) a += TWO_PI;
                     L.phi = a;
@@ -1720,6 +1822,29 @@ __global__ void clone_gathered_kernel(unsigned char* buf, long long stride, Gath
     dst.grid[o] = g[r]; dst.tcut[o] = g[stride + r];
     const uint8_t* b = block + (size_t)stride * 80;
     dst.down[o] = b[r]; dst.inj[o] = b[stride + r];
+}
+
+// End of the ion: fold the exact accumulators into the FP64 tally cells [c0, c1).  The words are first brought to their
+// unique form (0 <= word < 2^32 below the top one) so that the result is a function of the accumulated VALUE only, then
+// summed from the top down.
+__global__ void fold_accumulators_kernel(const long long* __restrict__ acc, size_t c0, size_t c1, double* tally) {
+    const size_t c = c0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    long long d[ACC_D];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < ACC_D; k++) { d[k] = acc[c * ACC_D + k]; any |= d[k] != 0; }
+    if (!any) { tally[c] = 0.0; return; }
+#pragma unroll
+    for (int k = 0; k + 1 < ACC_D; k++) {
+        const long long carry = d[k] >> 32;  // arithmetic shift = floor
+        d[k] -= carry << 32;
+        d[k + 1] += carry;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int k = ACC_D - 1; k >= 0; k--) v = fma((double)d[k], scalbn(1.0, ACC_ELO + 32 * k), v);
+    tally[c] = v;
 }
 
 // particle_counter.jl:81-85: shock-frame dN(p) of the cosmic rays = sum of the PSD over the angle bins

@@ -70,3 +70,18 @@ def test_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle_engine" not in txt and "mcs_oracle" not in txt, f
+
+
+def test_plain_c_caller_builds_and_runs(tmp_path):
+    """include/mcs.h from a C (not C++) translation unit of a third party: tests/c_caller.c is compiled with gcc -std=c99
+    -pedantic-errors, linked against the CPU oracle (same ABI as the CUDA library) and run through one pcut."""
+    import subprocess
+    exe = tmp_path / "c_caller"
+    odir = os.path.join(ROOT, "oracle")
+    cc = subprocess.run(["gcc", "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "c_caller.c"), "-o", str(exe), "-L", odir, "-lmcs_oracle", "-lm",
+                         f"-Wl,-rpath,{odir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "c_caller ok: backend cpu-oracle" in run.stdout

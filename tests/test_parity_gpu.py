@@ -115,9 +115,9 @@ def test_per_particle_parity_at_scale(olib, clib):
         for key in ("fate", "helix_count", "retro_steps", "n_draws"):
             assert np.array_equal(fo[key], fc[key]), f"pcut {k}: {key} differs in {(fo[key] != fc[key]).sum()} of {n}"
         assert (ns_o, st_o) == (ns_c, st_c)
-        # the gyro-phase is ill-conditioned where asin's argument sits at the clamp (slope ~1e4): over 1.8e5 particle-pcuts
-        # the worst case seen is 1.3e-8 of 2 pi, so the phase is held to 1e-7 here (1e-8 in the small cases)
-        compare_saved(run, sp, eo.get_population(1, n), ec.get_population(1, n), TOL_END_STATE, 1e-7)
+        # the gyro-phase is ill-conditioned near the poles of the pitch angle (module docstring): 1e-4 of 2 pi over
+        # 1.8e5 particle-pcuts, 1e-5 in the small cases
+        compare_saved(run, sp, eo.get_population(1, n), ec.get_population(1, n), TOL_END_STATE, 1e-4)
         total += st_o
         if ns_o == 0:
             break
@@ -360,15 +360,36 @@ def test_branch_free_sqrt_and_division_are_ieee(clib):
 
 
 def test_deterministic_tallies_run_to_run(clib):
-    """Default (static) schedule: the per-warp / per-block partials are reduced in a fixed order, so the flux tallies and
-    scalars are bitwise identical run to run (the PSD takes L2 atomics and is only required to agree to rounding)."""
-    run = problem.setup_run(problem.planar_test_particle_input(30_000, momentum_cutoffs=LADDER[:4]))
+    """Run-to-run determinism of EVERY tally (north_star).  Flux arrays, crossing counts and scalars: per-warp / per-block
+    partials reduced in a fixed order (default static schedule).  Phase-space histogram, escape PSDs, coupled spectra,
+    efficiency spectra and the energy pool: exact fixed-point accumulators (cfg.det_tallies, integer atomics), so their
+    bits do not depend on the order of the adds at all."""
+    run = problem.setup_run(problem.planar_test_particle_input(30_000, momentum_cutoffs=LADDER[:4], maximum_age=3.0e4,
+                                                               tcuts=[1e2, 3e2, 1e3, 3e3, 1e4, 1e6]))
     a = driver.main_loops(run, make_engine(clib, run), n_iters=1, want_log=False)[0][0]["tallies"]
     b = driver.main_loops(run, make_engine(clib, run), n_iters=1, want_log=False)[0][0]["tallies"]
-    for nm in ("pxx_flux", "pxz_flux", "energy_flux", "num_crossings"):
+    for nm in ("pxx_flux", "pxz_flux", "energy_flux", "num_crossings", "psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream",
+               "esc_energy_eff", "esc_num_eff", "weight_coupled", "spectra_coupled", "energy_transfer_pool"):
         assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
     assert a.scalars == b.scalars and a.stats == b.stats
-    assert rel_close(a.psd, b.psd, 0) < 1e-12
+    assert a.psd.sum() > 0 and a.weight_coupled.sum() > 0
+
+
+def test_exact_accumulators_are_schedule_independent_and_match_fp64_sums(clib):
+    """The exact accumulators against (i) a different particle-to-lane schedule (dynamic queue): bitwise equal histogram,
+    and (ii) the plain FP64 red path (det_tallies = 0): equal to summation order."""
+    run = problem.setup_run(problem.planar_test_particle_input(20_000, momentum_cutoffs=LADDER[:4]))
+    out = []
+    for det, dyn in ((1, 0), (1, 1), (0, 0)):
+        cfg = driver.make_config(clib, run, na_cr=1000)
+        cfg.det_tallies, cfg.dynamic_queue = det, dyn
+        out.append(driver.main_loops(run, abi.Engine(clib, cfg), n_iters=1, want_log=False)[0][0]["tallies"])
+    a, b, c = out
+    for nm in ("psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream", "esc_energy_eff", "esc_num_eff"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+        assert np.array_equal(getattr(a, nm) != 0, getattr(c, nm) != 0), nm
+        assert rel_close(getattr(a, nm), getattr(c, nm), 0) < 1e-12, nm
+    assert a.stats["n_errors"] == 0
 
 
 def test_dynamic_queue_schedule_gives_same_particles(clib):
@@ -434,3 +455,37 @@ def test_spectra_and_fluxes_statistical_parity(olib, clib):
         z_all.append(z)
     # the momentum spectrum's bins are nearly independent: its z scores must also look like draws from Student-t(R-1)
     assert stats.kstest(z_all[0], stats.t(df=R - 1).cdf).pvalue > 1e-3
+
+
+def test_two_iterations_with_profile_update(olib, clib):
+    """the flux hand-off to the smoother and back.  Two iterations of main_loops with a `profile_update`
+    callback that stands in for smooth_grid_par (it returns a smoothed precursor whose depth is set from the momentum
+    flux the library handed back, rounded as iter_finalize.jl:51-54 rounds it, so the callback is a pure function of the
+    hand-off on both sides): CUDA and oracle must agree iteration by iteration — the second iteration runs on the updated,
+    device-resident profile (mcs_set_profile per iteration, nine arrays of n_grid + 2 doubles)."""
+    inp = problem.nonlinear_input(1500, momentum_cutoffs=LADDER[:4], num_iterations=2)
+    run = problem.setup_run(inp)
+    seen = {}
+
+    def make_update(tag):
+        def update(run_, prof, per_ion):
+            flux = np.round(per_ion[0]["pxx_flux"] / run_.F_px_upstream, 13)       # iter_finalize.jl:51-54
+            seen.setdefault(tag, []).append(flux)
+            excess = float(np.clip(np.max(flux[: run_.i_shock]) - 1.0, 0.0, 0.5))  # crude: deeper precursor for more excess flux
+            return problem.synthetic_precursor(run_, r_sub=3.0 - excess, scale_rg=5.0)
+        return update
+
+    ro = driver.main_loops(run, make_engine(olib, run), n_iters=2, profile_update=make_update("o"), want_log=False)
+    rc = driver.main_loops(run, make_engine(clib, run), n_iters=2, profile_update=make_update("c"), want_log=False)
+    for it in range(2):
+        a, b = ro[it][0], rc[it][0]
+        assert np.array_equal(a["n_saved"], b["n_saved"]) and np.array_equal(a["n_used"], b["n_used"]), it
+        assert a["tallies"].stats["n_fate"] == b["tallies"].stats["n_fate"], it
+        assert a["tallies"].stats["n_helix_steps"] == b["tallies"].stats["n_helix_steps"], it
+        assert np.array_equal(a["tallies"].num_crossings, b["tallies"].num_crossings), it
+        for nm in ("pxx_flux", "pxz_flux", "energy_flux"):
+            assert rel_close(a[nm], b[nm], 0, atol_frac=1e-6) <= TOL_TALLY, (it, nm)
+        assert rel_close(a["tallies"].psd, b["tallies"].psd, 0) <= TOL_TALLY, it
+    # the rounded hand-off is what the smoother sees: identical on both sides, hence identical second-iteration profiles
+    assert np.array_equal(seen["o"][0], seen["c"][0])
+    assert ro[1][0]["tallies"].stats["n_helix_steps"] != ro[0][0]["tallies"].stats["n_helix_steps"]
