@@ -117,8 +117,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_arm(workload, sample_per_pcut, steps, warmup, threads, pcuts="bench", all_species=False):
-    """The reference's CPU implementation of the path = the C restatement (oracle/), all host threads."""
+def cpu_arm(workload, sample_per_pcut, steps, warmup, threads, pcuts="bench", all_species=False, collect=None):
+    """The reference's CPU implementation of the path = the C restatement (oracle/), all host threads.
+    `collect`: list that receives the ion-1 tallies of every timed step (each step then uses its own seed and injection
+    draw, i.e. the steps are independent replicas: bench.py's statistical-parity block)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_engine
     from mcs_b200 import abi, driver
@@ -128,14 +130,19 @@ def cpu_arm(workload, sample_per_pcut, steps, warmup, threads, pcuts="bench", al
     e = abi.Engine(lib, driver.make_config(lib, run, threads=threads, na_cr=1000))
     tot_steps, tot_t = 0, 0.0
     for it in range(warmup + steps):
+        if collect is not None:  # independent replica: another Philox key and another injection draw
+            e.close()
+            e = abi.Engine(lib, driver.make_config(lib, run, threads=threads, na_cr=1000, seed=7000 + it))
         t0 = time.perf_counter()
         res = driver.main_loops(run, e, n_iters=1, want_psd=True, want_log=False, shuffle_population=True,
-                                only_ions=None if all_species else [1])[0]
+                                only_ions=None if all_species else [1], pop_seed_offset=(1000 * (it + 1) if collect is not None else 0))[0]
         dt = time.perf_counter() - t0
         st = sum(r["tallies"].stats["n_helix_steps"] + r["tallies"].stats["n_retro_steps"] for r in res if r is not None)
         if it >= warmup:
             tot_steps += st
             tot_t += dt
+            if collect is not None:
+                collect.append(res[0]["tallies"])
     return tot_steps / tot_t, tot_t / max(steps, 1), tot_steps // max(steps, 1)
 
 
@@ -211,6 +218,9 @@ def main():
                     help="multi workload: one step = all ion species of the iteration (p, He, e-) with the pool hand-over")
     ap.add_argument("--cpu-sample", type=int, default=10000, help="particles per pcut of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stat-parity", type=int, default=0, metavar="R",
+                    help="cpu_baseline leg: run the CPU sample as R independent replicas (cpu-sample / R particles per pcut each) and "
+                         "report per-spectrum chi-square p-values of the GPU run against them (north_star 'full runs')")
     ap.add_argument("--no-verify", action="store_true", help="skip the N-rank vs 1-rank check that precedes a multi-GPU run")
     ap.add_argument("--generate-in-library", action="store_true",
                     help="SURVEY 8(f2): hand init_pop to the library in run-length form instead of copying host arrays")
@@ -425,9 +435,23 @@ def main():
         if verify is not None:
             out["verify"] = verify
         if world == 1 and not a.no_cpu_baseline:
-            v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads, a.pcuts, all_species)
-            out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
-                                   "sample": f"{a.cpu_sample} particles per pcut, full pcut ladder, {st} steps, {s_it:.1f} s"}
+            if a.stat_parity >= 4 and not all_species:
+                R, n_rep = a.stat_parity, max(a.cpu_sample // a.stat_parity, 500)
+                reps = []
+                v, s_it, st = cpu_arm(a.workload, n_rep, R, 0, threads, a.pcuts, False, collect=reps)
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import stat_parity
+                cmp_ = stat_parity.compare(stat_parity.observables(res[ions[0]]["t"], run), [stat_parity.observables(t, run) for t in reps],
+                                           n_ratio=a.n_per_pcut / n_rep)
+                out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+                                       "sample": f"{R} independent replicas of {n_rep} particles per pcut, full pcut ladder, {st} steps each, {s_it:.1f} s each",
+                                       "stat_parity": {"p_min_stated": 1e-3, "replicas": R, "particles_per_pcut_per_replica": n_rep,
+                                                       "method": "tests/stat_parity.py: per-bin z of the GPU run against the replica mean, chi-square p",
+                                                       "spectra": cmp_}}
+            else:
+                v, s_it, st = cpu_arm(a.workload, a.cpu_sample, 1, 0, threads, a.pcuts, all_species)
+                out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+                                       "sample": f"{a.cpu_sample} particles per pcut, full pcut ladder, {st} steps, {s_it:.1f} s"}
             # the reference loop itself is serial (the threading directive at main_loops.jl:227 is a comment): one thread too
             n1 = max(a.cpu_sample // 10, 200)
             v1, s1, st1 = cpu_arm(a.workload, n1, 1, 0, 1, a.pcuts, all_species)

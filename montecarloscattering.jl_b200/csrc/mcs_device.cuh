@@ -48,11 +48,13 @@
 #define MCS_FAST_MAX 256  // safety bound on consecutive fast passes
 #endif
 
-// Out-of-line cold functions follow the call ABI; MCS_INLINE_COLD folds them into their callers instead (tuning aid).
-#ifdef MCS_INLINE_COLD
-#define MCS_COLD __forceinline__
-#else
+// The event drain and the boost of the fast loop are folded into it: as ABI calls they forced the loop's state through
+// local memory around every call site (+6.7 % steps/s inlined, spill traffic 130 B -> 8 B; profiles/r02_*).
+// MCS_CALL_COLD restores the out-of-line form (tuning aid).
+#ifdef MCS_CALL_COLD
 #define MCS_COLD __noinline__
+#else
+#define MCS_COLD __forceinline__
 #endif
 
 namespace mcs {
@@ -989,6 +991,65 @@ __device__ __forceinline__ int push_events(const DevParams& P, const WarpMem& wm
     return qn;
 }
 
+// Converged: give every lane of `need` (idle, queue not yet found empty) the next particle of this warp's sequence —
+// chunks of 32 consecutive particles dealt round-robin to the warps (deterministic), or one atomic per warp on a global
+// queue head (dynamic) — and set up its record (particle_loop.jl:44-96, 131-153).
+template <bool DEBUG>
+__device__ __forceinline__ void refill_lanes(const DevParams& P, Lane& l, const unsigned need, const bool fast_ok) {
+    const int ng = P.n_grid;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const bool custom = P.flags & F_CUSTOM_EPSB, dynamic = P.flags & F_DYNAMIC_QUEUE;
+    const long long total_warps = (long long)gridDim.x * n_warps, gwarp = (long long)blockIdx.x * n_warps + warp;
+    const int rank = __popc(need & ((1u << lane) - 1u));
+    long long base;
+    if (dynamic) {
+        base = 0;
+        const int leader = __ffs(need) - 1;
+        if (lane == leader) base = (long long)atomicAdd(&P.t.counters[CNT_QUEUE], (unsigned long long)__popc(need));
+        base = __shfl_sync(FULL, base, leader);
+    } else {
+        base = l.next_j;
+        l.next_j += __popc(need);
+    }
+    if (!((need >> lane) & 1u)) return;
+    const long long j = base + rank;
+    const long long mine = dynamic ? j : ((j >> 5) * total_warps + gwarp) * 32 + (j & 31);
+    if (mine >= P.n_use) { l.queue_empty = true; return; }
+    const int ip = (int)mine;
+    l.ip = ip;
+    l.ptot = P.cur.ptot[ip]; l.pb = P.cur.pb[ip]; l.x = P.cur.x[ip];
+    const double xn_per = P.cur.xn_per[ip];
+    l.prp_x = P.cur.prp_x[ip]; l.acct = P.cur.acctime[ip]; l.phi = P.cur.phi[ip];
+    l.i_grid = (int)P.cur.grid[ip]; l.i_grid_old = l.i_grid; l.tcut = (int)P.cur.tcut[ip];
+    l.down = P.cur.down[ip]; l.inj = P.cur.inj[ip];
+    l.helix = 0; l.i_return = -1; l.t_step = 0.0; l.x_old_le0 = true; P.retro[ip] = 0;
+    l.xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
+    // A fresh particle needs nothing the fast loop cannot do, unless its record is outside what the loop itself
+    // produces (hand-made populations): those take the general pass first.
+    l.parked = !fast_ok || l.xsel > 1 || l.prp_x < P.x_grid_stop || (l.inj && l.x < P.feb_up) || (l.down && !l.inj && l.x < 0) ||
+               l.i_grid > ng;
+    l.gam_pf = hypot(1.0, l.ptot / P.mc);
+    l.gd = 1 / (P.zz * P.bt[l.i_grid]);
+    if (custom && l.x > P.x_grid_stop) l.gd *= sqrt(l.x / P.x_grid_stop);
+    l.grt = l.ptot * P.c * l.gd;
+    l.gper = TWO_PI * l.gam_pf * P.m * P.c * l.gd;
+    l.iz = l.i_grid;
+    const int iz = l.iz;
+    l.ux = P.ux[iz]; l.gsf = P.gsf[iz]; l.gef = P.gef[iz]; l.bsin = P.sinth[iz]; l.bcos = P.costh[iz];
+    l.pperp = perpendicular_momentum(P, l.ptot, l.pb);
+    l.gr = l.pperp * P.c * l.gd;
+    l.inv_ptot = 1 / l.ptot; l.inv_gm = 1 / (l.gam_pf * P.m);
+    l.rng_n = 0; l.rng_c1 = (uint32_t)(P.first_global + ip); l.rng_exhausted = false;
+    if (DEBUG) {
+        l.rng_ru = nullptr; l.rng_rn = 0;
+        if (P.replay_u != nullptr && ip < P.replay_n) {
+            l.rng_ru = P.replay_u + P.replay_off[ip];
+            l.rng_rn = P.replay_off[ip + 1] - P.replay_off[ip];
+        }
+        l.slot = P.trace_slot ? P.trace_slot[ip] : -1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // General section: refill idle lanes, then run ONE full helix-loop pass (particle_loop.jl:154-499) for every lane that
 // asked for it (`parked`), including everything rare: escapes, pcut save, tcuts, energy transfer, reflection, probability
@@ -1019,58 +1080,12 @@ __device__ __noinline__ bool general_section(const DevParams& P, Lane& Lref, con
 
     for (;;) {
         // ---- refill idle lanes ---------------------------------------------------------------------
-        unsigned need = __ballot_sync(FULL, ip < 0 && !queue_empty);
-        if (need != 0u) {
-            const int rank = __popc(need & ((1u << lane) - 1u));
-            long long base;
-            if (dynamic) {  // one atomic per warp on the global queue head
-                base = 0;
-                const int leader = __ffs(need) - 1;
-                if (lane == leader) base = (long long)atomicAdd(&P.t.counters[CNT_QUEUE], (unsigned long long)__popc(need));
-                base = __shfl_sync(FULL, base, leader);
-            } else {  // deterministic: chunks of 32 consecutive particles dealt round-robin to the warps
-                base = next_j;
-                next_j += __popc(need);
-            }
-            if (ip < 0 && !queue_empty) {
-                long long j = base + rank;
-                long long mine = dynamic ? j : ((j >> 5) * total_warps + gwarp) * 32 + (j & 31);
-                if (mine < P.n_use) {
-                    ip = (int)mine;
-                    // particle_loop.jl:44-96, 131-153
-                    ptot = P.cur.ptot[ip]; pb = P.cur.pb[ip]; x = P.cur.x[ip];
-                    const double xn_per = P.cur.xn_per[ip];
-                    prp_x = P.cur.prp_x[ip]; acct = P.cur.acctime[ip]; phi = P.cur.phi[ip];
-                    i_grid = (int)P.cur.grid[ip]; i_grid_old = i_grid; tcut = (int)P.cur.tcut[ip];
-                    down = P.cur.down[ip]; inj = P.cur.inj[ip];
-                    helix = 0; i_return = -1; t_step = 0.0; x_old_le0 = true; P.retro[ip] = 0;
-                    xsel = xn_per == P.xn_fine ? 0 : (xn_per == P.xn_coarse ? 1 : 2);
-                    // A fresh particle needs nothing the fast loop cannot do, unless its record is outside what the
-                    // loop itself produces (hand-made populations): those take the general pass first.
-                    parked = !fast_ok || xsel > 1 || prp_x < P.x_grid_stop || (inj && x < P.feb_up) || (down && !inj && x < 0) ||
-                             i_grid > ng;
-                    gam_pf = hypot(1.0, ptot / P.mc);
-                    gd = 1 / (P.zz * P.bt[i_grid]);
-                    if (custom && x > P.x_grid_stop) gd *= sqrt(x / P.x_grid_stop);
-                    grt = ptot * P.c * gd;
-                    gper = TWO_PI * gam_pf * P.m * P.c * gd;
-                    iz = i_grid;
-                    ux = P.ux[iz]; gsf = P.gsf[iz]; gef = P.gef[iz]; bsin = P.sinth[iz]; bcos = P.costh[iz];
-                    pperp = perpendicular_momentum(P, ptot, pb);
-                    gr = pperp * P.c * gd;
-                    inv_ptot = 1 / ptot; inv_gm = 1 / (gam_pf * P.m);
-                    rng.n = 0; rng.c1 = (uint32_t)(P.first_global + ip); rng.exhausted = false;
-                    if (DEBUG) {
-                        rng.ru = nullptr; rng.rn = 0;
-                        if (P.replay_u != nullptr && ip < P.replay_n) {
-                            rng.ru = P.replay_u + P.replay_off[ip];
-                            rng.rn = P.replay_off[ip + 1] - P.replay_off[ip];
-                        }
-                        slot = P.trace_slot ? P.trace_slot[ip] : -1;
-                    }
-                } else {
-                    queue_empty = true;
-                }
+        {
+            const unsigned need = __ballot_sync(FULL, ip < 0 && !queue_empty);
+            if (need != 0u) {
+                l.rng_n = rng.n; l.rng_c1 = rng.c1; l.rng_exhausted = rng.exhausted; l.rng_ru = rng.ru; l.rng_rn = rng.rn;
+                refill_lanes<DEBUG>(P, l, need, fast_ok);
+                rng.n = l.rng_n; rng.c1 = l.rng_c1; rng.exhausted = l.rng_exhausted; rng.ru = l.rng_ru; rng.rn = l.rng_rn;
             }
         }
         if (__all_sync(FULL, ip < 0)) { all_done = true; break; }
@@ -1333,6 +1348,7 @@ enum : uint32_t {
     ST_MUSN = 512u,  // mu / sn are newer than the record's pb / pperp
     ST_PHI = 1024u,  // the phase registers are newer than the record's angle (a boost without a committed pass after it)
     ST_ETF = 2048u,  // energy transfer is due before the next pass (particle_loop.jl:235): general pass
+    ST_QEMPTY = 4096u,  // this lane found the warp's particle sequence exhausted
 };
 constexpr double COS_AT_LIMIT = 1.4901161193847656e-08;  // sqrt(1 - prevfloat(1.0)^2): cosine of the phase change at the clamp
 
@@ -1430,41 +1446,53 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
             // when enough lanes wait, the warp leaves for the general section.  Per particle the sequence of operations
             // is the one of particle_loop.jl.  Register state: position, pitch (mu, sn = pb, pperp over ptot), phase,
             // clock, PRP, and three per-momentum constants; zone constants come from the shared zone table.
-            const int ip = L.ip;
-            const bool live = ip >= 0;  // after the general section every lane with a particle runs
-            double x = L.x, acct = L.acct, prp_x = L.prp_x, grt = L.grt, t_step = L.t_step;
-            double mu = L.pb * L.inv_ptot, sn = L.pperp * L.inv_ptot;
-            double vgm = L.ptot * L.inv_gm;
-            double gper = (ELECTRON && L.ptot < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * L.gd : TWO_PI * L.gam_pf * P.mc * L.gd;
+            int ip;
+            double x, acct, prp_x, grt, t_step, mu, sn, vgm, gper;
             double cph, sph;  // gyro-phase as (cos, sin): the kick and the advance are rotations, no asin / mod2pi per pass
-            sincos(L.phi, &sph, &cph);
-            int iz = L.iz, helix = L.helix, qn = L.qn;
-            uint32_t gpack = (uint32_t)L.i_grid | ((uint32_t)L.i_grid_old << 16);
-            uint32_t rng_n = L.rng_n, rng_s2 = L.rng_s2, rng_s3 = L.rng_s3;
-            const uint32_t rng_c1 = L.rng_c1;
-            // status word; ST_PRE = "the general pass must see this particle before its next pass" for the reasons that only
-            // change at a boost, a shock crossing or a zone change (momentum above a cut-off, pending energy transfer)
-            uint32_t st = (L.down ? ST_DOWN : 0u) | (L.inj ? ST_INJ : 0u) | (L.x_old_le0 ? ST_XOLDLE0 : 0u) | (L.xsel ? ST_XSEL : 0u) |
-                          (L.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) | (L.ptot > P.pcut ? ST_GTPCUT : 0u);
-            if (P.energy_transfer_frac > 0 && !L.inj && L.x_old_le0 && L.i_grid_old != L.i_grid) st |= ST_ETF;
-            // The Philox block of the NEXT pass is produced during the current one (integer pipe, independent of the
-            // FP64 chain): q* = block (rng_n + odd) / 2 of this particle's stream.
+            int iz, helix;
+            uint32_t gpack, rng_n, rng_s2, rng_s3, rng_c1;
+            // status word; ST_GTPMAX / ST_GTPCUT / ST_ETF = "the general pass must see this particle before its next pass"
+            // for the reasons that only change at a boost, a shock crossing or a zone change
+            uint32_t st;
+            // registers <- record (at entry, and for a lane refilled inside the loop)
+#define MCS_LOAD_LANE()                                                                                                     \
+    do {                                                                                                                    \
+        ip = L.ip;                                                                                                          \
+        x = L.x; acct = L.acct; prp_x = L.prp_x; grt = L.grt; t_step = L.t_step;                                            \
+        mu = L.pb * L.inv_ptot; sn = L.pperp * L.inv_ptot;                                                                  \
+        vgm = L.ptot * L.inv_gm;                                                                                            \
+        gper = (ELECTRON && L.ptot < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * L.gd : TWO_PI * L.gam_pf * P.mc * L.gd;    \
+        sincos(L.phi, &sph, &cph);                                                                                          \
+        iz = L.iz; helix = L.helix;                                                                                         \
+        gpack = (uint32_t)L.i_grid | ((uint32_t)L.i_grid_old << 16);                                                        \
+        rng_n = L.rng_n; rng_s2 = L.rng_s2; rng_s3 = L.rng_s3; rng_c1 = L.rng_c1;                                           \
+        st = (L.down ? ST_DOWN : 0u) | (L.inj ? ST_INJ : 0u) | (L.x_old_le0 ? ST_XOLDLE0 : 0u) | (L.xsel ? ST_XSEL : 0u) |  \
+             (L.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) | (L.ptot > P.pcut ? ST_GTPCUT : 0u) | (L.queue_empty ? ST_QEMPTY : 0u) | \
+             ((L.ip >= 0 && L.parked) ? ST_PARKED : 0u);                                                                     \
+        if (P.energy_transfer_frac > 0 && !L.inj && L.x_old_le0 && L.i_grid_old != L.i_grid) st |= ST_ETF;                  \
+    } while (0)
+            MCS_LOAD_LANE();
+            int qn = L.qn;
 #ifdef MCS_PREFETCH
             uint32_t q0, q1, q2, q3;
             philox4x32_10_rk((rng_n + (rng_n & 1u)) >> 1, rng_c1, P.ctr2, P.ctr3, P.rk, q0, q1, q2, q3);
 #endif
-            const int n_act = __popc(__ballot_sync(FULL, live));
-            const int park_t = min(MCS_PARK_T, (3 * n_act + 3) >> 2);
+            int n_act = __popc(__ballot_sync(FULL, ip >= 0));
+            int park_t = min(MCS_PARK_T, (3 * n_act + 3) >> 2);
             int psp_debt = 0, wait_debt = 0;
             for (int it = 0; it < MCS_FAST_MAX; it++) {
                 uint32_t fev = 0;   // crossing event produced by this pass
                 int ev_old = 0;     // its zone before the move
-                if (live && !(st & (ST_PARKED | ST_NEEDPSP))) {
+                if (ip >= 0 && !(st & (ST_PARKED | ST_NEEDPSP))) {
                     const int ig = (int)(gpack & 0xffffu);
                     // what the general pass must see before this pass: helix cap, a momentum above a cut-off (saved when
                     // downstream), pending energy transfer, age
-                    bool park = (helix >= P.helix_cap) || (st & (ST_GTPMAX | ST_ETF)) || ((st & (ST_DOWN | ST_GTPCUT)) == (ST_DOWN | ST_GTPCUT));
+                    bool park = (helix >= P.helix_cap) || (st & (ST_GTPMAX | ST_ETF));
                     if (P.age_max > 0) park = park || acct > P.age_max;
+                    // downstream and above this pcut: the particle is saved by its next pass (particle_loop.jl:361-380): general pass.
+                    // (Saving and refilling inside this loop was tried — MCS_TAIL, profiles/r02_variants.md — and lost 8 %:
+                    // the extra vote per iteration and the larger loop cost more than the idle lanes it removed.)
+                    park = park || ((st & (ST_DOWN | ST_GTPCUT)) == (ST_DOWN | ST_GTPCUT));
                     if (ig != iz && !park) {
                         // Code Block 3 zone change (particle_loop.jl:186-228): without a change of flow speed only the
                         // zone's constants change; with one, the momentum must be boosted (batched below)
@@ -1531,7 +1559,8 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         // Is this a plain pass?  Same zone, and inside the grid or between its end and the PRP.
                         const bool dn = x_n > x;
                         const bool same = dn ? (zc.y > x_n) : (zc.x <= x_n);
-                        bool rare = !same | !(sn2 > 0.0) | park | ((x_n >= P.x_grid_stop) & ((x < P.x_grid_stop) | (x_n >= prp_x) | ELECTRON));
+                        bool rare = !same | !(sn2 > 0.0) | park |
+                                    ((x_n >= P.x_grid_stop) & ((x < P.x_grid_stop) | (x_n >= prp_x) | ELECTRON));
                         if (st & ST_INJ) rare |= x_n < P.feb_up;
                         if (P.feb_dn > 0) rare |= x_n > P.feb_dn;
                         if (reflect_cfg) rare |= (x_n <= 0) & (x > 0);
@@ -1592,8 +1621,8 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                             mu = cos_new; sn = sin_new; cph = cph_n; sph = sph_n; x = x_n;
                             gpack = (uint32_t)ig_new | ((uint32_t)iz << 16);
                             rng_n += 2; rng_s2 = l2; rng_s3 = l3;
-                        } else {
-                            st |= ST_PARKED;  // (the prefetched block is stale now; it is rebuilt when the lane re-enters the loop)
+                        } else if (ip >= 0) {
+                            st |= ST_PARKED;  // (a prefetched block is stale now; it is rebuilt when the lane re-enters the loop)
                         }
                     } else if (park) {
                         st |= ST_PARKED;
@@ -1609,7 +1638,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                     const unsigned mp = __ballot_sync(FULL, (st & ST_NEEDPSP) != 0u);
                     if (mp) {
                         const int n_psp = __popc(mp);
-                        const int n_run = __popc(__ballot_sync(FULL, live && !(st & (ST_PARKED | ST_NEEDPSP))));
+                        const int n_run = __popc(__ballot_sync(FULL, ip >= 0 && !(st & (ST_PARKED | ST_NEEDPSP))));
                         psp_debt += n_psp;
                         if (psp_debt >= MCS_PSP_DEBT || MCS_PSP_NUM * n_psp >= n_run) {
                             psp_debt = 0;
@@ -1641,7 +1670,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                     }
                 }
                 MCS_SC(c_fast_iter++;)
-                const int n_wait = __popc(__ballot_sync(FULL, live && (st & ST_PARKED)));
+                const int n_wait = __popc(__ballot_sync(FULL, ip >= 0 && (st & ST_PARKED)));
                 if (n_wait > 0 && n_wait >= park_t) break;
 #if MCS_WAIT_DEBT > 0
                 // few lanes waiting for a long time cost as much as many lanes waiting briefly: also leave once the
@@ -1651,7 +1680,9 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
 #endif
             }
             // ---- back to the record ----
-            if (live) {
+            L.ip = ip;
+            if (st & ST_QEMPTY) L.queue_empty = true;
+            if (ip >= 0) {
                 L.x = x; L.acct = acct; L.prp_x = prp_x; L.t_step = t_step; L.gper = gper;
                 if (st & ST_PHI) {  // last touched by a boost: atan(...) - pi/2 lies in (-3 pi/2, pi/2] (transformers.jl:603-604)
                     double a = atan2(sph, cph);

@@ -146,7 +146,7 @@ def reduce_tallies_host(t: abi.Tallies, comm) -> abi.Tallies:
 def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = None, comm=None,
                device_comm: bool = False, want_psd: bool = True, want_log: bool = True, profile_update=None,
                host_pcut_loop: bool = False, shuffle_population: bool = False, generate_in_library: bool = False,
-               only_ions=None):
+               only_ions=None, pop_seed_offset: int = 0):
     """loop_itr / loop_ion / loop_pcut of main_loops.jl:52-341.
 
     Returns a list (per iteration) of lists (per ion) of dicts with the per-ion tallies (pure sums),
@@ -177,7 +177,7 @@ def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = No
                 engine.begin_ion_generate(i_iter, i_ion, species_struct(run, i_ion), ip, first_global=lo, n_local=hi - lo,
                                           shuffle=shuffle_population)
             else:
-                rng = np.random.default_rng((i_iter - 1) * run.n_ions + (i_ion - 1))  # stands in for :120-121
+                rng = np.random.default_rng((i_iter - 1) * run.n_ions + (i_ion - 1) + pop_seed_offset)  # stands in for :120-121
                 ip = problem.init_pop(run, prof, i_ion, rng, shuffle=shuffle_population)
                 n = len(ip.pop["weight"])
                 lo, hi = shard_bounds(n, rank, world)

