@@ -191,6 +191,8 @@ def verify_multi_rank(lib, dist, rank, world, local_rank):
                                    and ta.stats["n_retro_steps"] == tb.stats["n_retro_steps"],
             "num_crossings_equal": bool(np.array_equal(ta.num_crossings, tb.num_crossings)),
             "psd_bitwise_equal": bool(np.array_equal(ta.psd, tb.psd)),
+            "fluxes_bitwise_equal": bool(np.array_equal(ta.pxx_flux, tb.pxx_flux) and np.array_equal(ta.pxz_flux, tb.pxz_flux)
+                                         and np.array_equal(ta.energy_flux, tb.energy_flux)),
             "max_rel_diff": {"pxx_flux": rel(ta.pxx_flux, tb.pxx_flux), "pxz_flux": rel(ta.pxz_flux, tb.pxz_flux),
                              "energy_flux": rel(ta.energy_flux, tb.energy_flux), "psd": rel(ta.psd, tb.psd),
                              "esc_psd_feb_downstream": rel(ta.esc_psd_feb_downstream, tb.esc_psd_feb_downstream)},

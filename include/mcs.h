@@ -113,12 +113,16 @@ typedef struct McsConfig {
     int32_t threads;    /* CPU oracle only: OpenMP threads (0/1 = serial, ordered) */
     int32_t bin_thermal; /* also bin every thermal crossing on the fly (McsTallies.therm_d2N_*) so that the
                             unbounded crossing log is not needed: 0 = off, 1 = on */
-    int32_t dynamic_queue; /* 0 = particles dealt to warps in a fixed interleaved order (run-to-run deterministic tallies);
-                              1 = global atomic work queue (load-balanced, summation order varies) */
-    int32_t det_tallies;   /* 1 (default) = the phase-space histogram, escape PSDs, coupled spectra, x_spec spectra and the
-                              energy pool are accumulated as exact fixed-point sums (integer atomics on 8 x 32-bit digits per
+    int32_t dynamic_queue; /* 0 (default) = particles dealt to warps in a fixed interleaved order: the flux arrays and scalars, summed
+                              per warp and then over warps and blocks in a fixed order, are bitwise reproducible run to run;
+                              1 = global atomic work queue (idle lanes take the next particles: +4 % steps/s, the order of the
+                              flux sums then varies in the last bits).  Per-particle results and the exact-accumulator tallies
+                              (det_tallies) do not depend on it. */
+    int32_t det_tallies;   /* 1 (default) = the phase-space histogram, escape PSDs, coupled / x_spec / efficiency spectra and the
+                              energy pool are accumulated as exact fixed-point sums (integer atomics on 10 x 32-bit digits per
                               cell): bitwise identical run to run, for any schedule and any number of GPUs;
-                              0 = red.global.add.f64 (summation order varies in the last bits).  CUDA library only. */
+                              0 = red.global.add.f64 (order of the adds varies in the last bits).  CUDA library only.
+                              The flux arrays and scalars use ordered per-warp partials in either case (see dynamic_queue). */
 } McsConfig;
 
 /* Per-species scalars read inside the loop (main_loops.jl:97-100, utils.jl:72-96). */

@@ -284,7 +284,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     P.flags = (cfg->do_rad_losses ? F_RAD_LOSSES : 0) | (cfg->do_retro ? F_RETRO : 0) | (cfg->do_tcuts ? F_TCUTS : 0) |
               (cfg->dont_DSA ? F_DONT_DSA : 0) | (cfg->dont_scatter ? F_DONT_SCATTER : 0) |
               (cfg->use_custom_epsB ? F_CUSTOM_EPSB : 0) | ((cfg->compat & MCS_COMPAT_RETRO_KEEP_NEW_PITCH) ? F_KEEP_NEW_PITCH : 0) |
-              ((cfg->dynamic_queue || env_int("MCS_DYNAMIC_QUEUE", 0)) ? F_DYNAMIC_QUEUE : 0) |
+              (env_int("MCS_DYNAMIC_QUEUE", cfg->dynamic_queue) ? F_DYNAMIC_QUEUE : 0) |
               (env_int("MCS_NO_FAST_LOOP", 0) ? F_NO_FAST_LOOP : 0);
     {   // per-xn_per scattering constants, host libm (scattering.jl:46-60: the gyroradius cancels in vp_tg / lambda_mfp)
         const double xn[2] = {cfg->xn_per_fine, cfg->xn_per_coarse};
@@ -312,6 +312,7 @@ extern "C" int mcs_create(const McsConfig* cfg, McsHandle** out) {
     t.therm_sf = cfg->bin_thermal ? b + h->off_thsf : nullptr; t.therm_pf = cfg->bin_thermal ? b + h->off_thpf : nullptr;
     t.dndp_cr = cfg->bin_thermal ? b + h->off_dndp : nullptr;
     t.acc = h->d_acc; t.tally_base = h->d_tally;
+    t.pxx = b + h->off_pxx; t.pxz = b + h->off_pxz; t.efl = b + h->off_efl; t.scal = b + h->off_scal;
     t.counters = h->d_u64 + ng;
     t.ncross = h->d_u64;
     t.tg = h->d_tg; t.tpx = h->d_tpx; t.tpt = h->d_tpt; t.tw = h->d_tw; t.na_cr = cfg->na_cr;

@@ -117,6 +117,7 @@ struct TallyPtrs {
     long long* tg;          // thermal-crossing log
     double *tpx, *tpt, *tw;
     long long na_cr;
+    double *pxx, *pxz, *efl, *scal;  // flux arrays [n_grid] and scalars [SC_N] inside the packed tally buffer
     long long* acc;              // exact fixed-point accumulators, ACC_D digits per cell of the packed tally buffer, or null
     const double* tally_base;    // first cell of the packed FP64 tally buffer (cell index = pointer - tally_base)
     unsigned long long* ncross;  // [n_grid] thermal crossings per zone (integer adds: any order gives the same bits)
@@ -374,11 +375,12 @@ __device__ __forceinline__ double sqrt_guard(const DevParams& P, double a) {
 }
 
 // get_psd_bins.jl:16-39
-__device__ __forceinline__ int psd_bin_momentum(const DevParams& P, double ptot_sk) {
+// `uses`: how many call sites of the reference this one evaluation stands for (each would have warned on its own)
+__device__ __forceinline__ int psd_bin_momentum(const DevParams& P, double ptot_sk, int uses = 1) {
     int bin;
     if (ptot_sk < P.psd_mom_min) bin = 0;
     else bin = (int)trunc(log10(ptot_sk / P.psd_mom_min) * P.bpd_mom) + 1;
-    if (bin > P.M) { count(P, CNT_W_PSDMOM); bin = P.M; }
+    if (bin > P.M) { count(P, CNT_W_PSDMOM, (unsigned long long)uses); bin = P.M; }
     return bin;
 }
 // get_psd_bins.jl:73-97
@@ -953,6 +955,7 @@ __device__ __noinline__ ColdIO reflect_loop(const DevParams& P, ColdIO io, doubl
 // run at 64-80 registers (24-32 warps per SM): with the general pass inlined next to it the allocation was 128
 // registers with spills inside the loop (profiles/r01_v13_*).
 struct Lane {
+    double mu, sn, cph, sph;  // the fast loop's pitch and phase registers, kept across sections while cs_valid (see below)
     double ptot, pb, pperp, x, prp_x, acct, phi;
     double gam_pf, gd, grt, gr, gper, t_step, inv_ptot, inv_gm;
     double ux, gsf, gef, bsin, bcos;
@@ -961,6 +964,12 @@ struct Lane {
     int ip, next_j, iz, i_grid, i_grid_old, helix, tcut, i_return, xsel, slot, qn;
     uint32_t rng_n, rng_s2, rng_s3, rng_c1;
     bool rng_exhausted, queue_empty, down, inj, x_old_le0, parked;
+    // A lane that leaves the fast loop WITHOUT needing the general pass (the warp left because of other lanes) must come
+    // back with bit-identical registers: pb = ptot * mu -> mu = pb / ptot is not the identity, and how often a warp leaves
+    // depends on which particles share it.  With the registers kept here a particle's arithmetic depends on nothing but
+    // itself, so per-particle results are the same for any schedule and any number of GPUs.
+    bool cs_valid;
+    uint32_t cs_flags;  // ST_RAN | ST_MUSN | ST_PHI carried along
 };
 
 // Converged: append the lanes' events (ev != 0) to the warp's queue, drain a full batch.  Returns the new queue length.
@@ -1040,6 +1049,7 @@ __device__ __forceinline__ void refill_lanes(const DevParams& P, Lane& l, const 
     l.gr = l.pperp * P.c * l.gd;
     l.inv_ptot = 1 / l.ptot; l.inv_gm = 1 / (l.gam_pf * P.m);
     l.rng_n = 0; l.rng_c1 = (uint32_t)(P.first_global + ip); l.rng_exhausted = false;
+    l.cs_valid = false; l.cs_flags = 0u;
     if (DEBUG) {
         l.rng_ru = nullptr; l.rng_rn = 0;
         if (P.replay_u != nullptr && ip < P.replay_n) {
@@ -1098,6 +1108,7 @@ __device__ __noinline__ bool general_section(const DevParams& P, Lane& Lref, con
         double x_old = 0.0;    // position before this pass's move
         const bool served = ip >= 0 && parked;
         if (served) {
+            l.cs_valid = false;
             helix++;
             if (MCS_UNLIKELY(helix > P.helix_cap)) {
                 fin = 1;  // K-1
@@ -1429,6 +1440,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
     L.slot = -1; L.qn = 0;
     L.rng_n = 0; L.rng_s2 = 0; L.rng_s3 = 0; L.rng_c1 = 0;
     L.rng_exhausted = false; L.queue_empty = false; L.down = false; L.inj = false; L.x_old_le0 = true; L.parked = true;
+    L.mu = 0; L.sn = 1; L.cph = 1; L.sph = 0; L.cs_valid = false; L.cs_flags = 0u;
 #ifdef MCS_SCHED_COUNTERS
     unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_sections = 0;
 #define MCS_SC(x) x
@@ -1459,16 +1471,16 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
     do {                                                                                                                    \
         ip = L.ip;                                                                                                          \
         x = L.x; acct = L.acct; prp_x = L.prp_x; grt = L.grt; t_step = L.t_step;                                            \
-        mu = L.pb * L.inv_ptot; sn = L.pperp * L.inv_ptot;                                                                  \
         vgm = L.ptot * L.inv_gm;                                                                                            \
         gper = (ELECTRON && L.ptot < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * L.gd : TWO_PI * L.gam_pf * P.mc * L.gd;    \
-        sincos(L.phi, &sph, &cph);                                                                                          \
+        if (L.cs_valid) { mu = L.mu; sn = L.sn; cph = L.cph; sph = L.sph; }                                                 \
+        else { mu = L.pb * L.inv_ptot; sn = L.pperp * L.inv_ptot; sincos(L.phi, &sph, &cph); }                              \
         iz = L.iz; helix = L.helix;                                                                                         \
         gpack = (uint32_t)L.i_grid | ((uint32_t)L.i_grid_old << 16);                                                        \
         rng_n = L.rng_n; rng_s2 = L.rng_s2; rng_s3 = L.rng_s3; rng_c1 = L.rng_c1;                                           \
         st = (L.down ? ST_DOWN : 0u) | (L.inj ? ST_INJ : 0u) | (L.x_old_le0 ? ST_XOLDLE0 : 0u) | (L.xsel ? ST_XSEL : 0u) |  \
              (L.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) | (L.ptot > P.pcut ? ST_GTPCUT : 0u) | (L.queue_empty ? ST_QEMPTY : 0u) | \
-             ((L.ip >= 0 && L.parked) ? ST_PARKED : 0u);                                                                     \
+             ((L.ip >= 0 && L.parked) ? ST_PARKED : 0u) | (L.cs_valid ? L.cs_flags : 0u);                                   \
         if (P.energy_transfer_frac > 0 && !L.inj && L.x_old_le0 && L.i_grid_old != L.i_grid) st |= ST_ETF;                  \
     } while (0)
             MCS_LOAD_LANE();
@@ -1632,15 +1644,23 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                 if (__any_sync(FULL, fev != 0u))
                     qn = push_events(P, wm, qn, fev, ip, L.ptot * mu, L.ptot * sn, L.gam_pf, cph, sph, L.ptot, (int)(gpack & 0xffffu), ev_old,
                                      ev_old);
+                // leave the loop?  Enough lanes wait for the general pass, or few have waited long (short trajectories: many
+                // refills), or the bound on consecutive iterations is reached
+                MCS_SC(c_fast_iter++;)
+                const int n_wait = __popc(__ballot_sync(FULL, ip >= 0 && (st & ST_PARKED)));
+                wait_debt += n_wait;
+                const bool leaving = (n_wait > 0 && n_wait >= park_t) || (MCS_WAIT_DEBT > 0 && wait_debt >= MCS_WAIT_DEBT) ||
+                                     it == MCS_FAST_MAX - 1;
                 {   // converged: pending boosts.  Waiting costs idle lanes, serving costs the whole warp ~250 issue slots:
                     // serve once the lanes have waited MCS_PSP_DEBT lane-iterations in total, or when fewer lanes run
-                    // than wait.
+                    // than wait — and always before leaving: a boost asked for in this loop is done by this loop, so WHICH
+                    // of the two (mathematically equal) boost routines a particle meets never depends on its warp mates.
                     const unsigned mp = __ballot_sync(FULL, (st & ST_NEEDPSP) != 0u);
                     if (mp) {
                         const int n_psp = __popc(mp);
                         const int n_run = __popc(__ballot_sync(FULL, ip >= 0 && !(st & (ST_PARKED | ST_NEEDPSP))));
                         psp_debt += n_psp;
-                        if (psp_debt >= MCS_PSP_DEBT || MCS_PSP_NUM * n_psp >= n_run) {
+                        if (leaving || psp_debt >= MCS_PSP_DEBT || MCS_PSP_NUM * n_psp >= n_run) {
                             psp_debt = 0;
                             if (st & ST_NEEDPSP) {
                                 st &= ~ST_NEEDPSP;
@@ -1669,31 +1689,31 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         }
                     }
                 }
-                MCS_SC(c_fast_iter++;)
-                const int n_wait = __popc(__ballot_sync(FULL, ip >= 0 && (st & ST_PARKED)));
-                if (n_wait > 0 && n_wait >= park_t) break;
-#if MCS_WAIT_DEBT > 0
-                // few lanes waiting for a long time cost as much as many lanes waiting briefly: also leave once the
-                // waiting lanes have idled MCS_WAIT_DEBT lane-iterations in total (short trajectories: many refills)
-                wait_debt += n_wait;
-                if (wait_debt >= MCS_WAIT_DEBT) break;
-#endif
+                if (leaving) break;
             }
             // ---- back to the record ----
             L.ip = ip;
             if (st & ST_QEMPTY) L.queue_empty = true;
             if (ip >= 0) {
                 L.x = x; L.acct = acct; L.prp_x = prp_x; L.t_step = t_step; L.gper = gper;
-                if (st & ST_PHI) {  // last touched by a boost: atan(...) - pi/2 lies in (-3 pi/2, pi/2] (transformers.jl:603-604)
-                    double a = atan2(sph, cph);
-                    if (a > HALF_PI) a -= TWO_PI;
-                    L.phi = a;
-                } else if (st & ST_RAN) {  // last touched by a move: Base.mod2pi leaves it in [0, 2 pi)
-                    double a = atan2(sph, cph);
-                    if (a < 0.0) a += TWO_PI;
-                    L.phi = a;
+                if (st & (ST_PARKED | ST_NEEDPSP)) {
+                    // the general pass takes this particle next: give it the record in the reference's terms
+                    if (st & ST_PHI) {  // last touched by a boost: atan(...) - pi/2 lies in (-3 pi/2, pi/2] (transformers.jl:603-604)
+                        double a = atan2(sph, cph);
+                        if (a > HALF_PI) a -= TWO_PI;
+                        L.phi = a;
+                    } else if (st & ST_RAN) {  // last touched by a move: Base.mod2pi leaves it in [0, 2 pi)
+                        double a = atan2(sph, cph);
+                        if (a < 0.0) a += TWO_PI;
+                        L.phi = a;
+                    }
+                    if (st & ST_MUSN) { L.pb = L.ptot * mu; L.pperp = L.ptot * sn; }
+                    L.cs_valid = false;
+                } else {
+                    // the warp left because of other lanes: this one comes back with exactly these registers
+                    L.mu = mu; L.sn = sn; L.cph = cph; L.sph = sph;
+                    L.cs_valid = true; L.cs_flags = st & (ST_RAN | ST_MUSN | ST_PHI);
                 }
-                if (st & ST_MUSN) { L.pb = L.ptot * mu; L.pperp = L.ptot * sn; }
                 if (st & ST_RAN) L.i_return = 2;
                 L.helix = helix;
                 L.i_grid = (int)(gpack & 0xffffu); L.i_grid_old = (int)(gpack >> 16);
