@@ -300,6 +300,29 @@ MCS_API int mcs_run_ion(McsHandle* h, const double* pcuts, int32_t n_pcuts, doub
 /* Finish an ion: sum tallies over ranks (NCCL) and copy them to the caller's arrays. */
 MCS_API int mcs_end_ion(McsHandle* h, McsTallies* out);
 
+/* the pressure consumer of the tallies, thermo_calcs (/root/reference/src/thermo_calcs.jl:31-355, called from
+ * ion_finalize.jl:38-47), evaluated where the PSD lives instead of shipping (M+2)(T+2)n_grid doubles to the host first.
+ * Per zone: d2N_pf = 1e-99 + thermal crossings boosted to the plasma frame (McsTallies.therm_d2N_pf, :133-164) + every CR
+ * cell of psd re-binned by the boost of its bin centre (:178-207); normalised to zone_pop (:209-226); then the three
+ * normalisation cases and the pressure / energy-density sums (:242-352).  Needs cfg.bin_thermal = 1 and the tallies of an
+ * ended ion (mcs_end_ion) unless the three input arrays below are given.  Species constants (aa, zz unused, T0, n0) are the
+ * McsSpecies of the last mcs_begin_ion; beta0/gam0 and the bin geometry are the McsConfig's. */
+typedef struct McsThermoIn {
+    const double* cos_center; /* [T+1]  -(cos_lo + cos_hi)/2 of angle bin jth = 0..T          thermo_calcs.jl:59-75  */
+    const double* pt_center;  /* [M+1]  centre momentum [g cm/s] of bin k = 0..M              thermo_calcs.jl:77-82  */
+    const double* zone_pop;   /* [n_grid] particles per zone, set_grid_volumes!      particle_counter.jl:1463-1523   */
+    double temperature_K;     /* T0_ion[i_ion] (McsSpecies carries no temperature)                                   */
+    /* optional HOST arrays replacing the device-resident tallies (NULL = use the ion just ended); layouts of McsTallies */
+    const double* psd;            /* [(M+2)(T+2)n_grid] */
+    const double* therm_d2N_pf;   /* [(T+2)(M+2)n_grid] */
+    const int64_t* num_crossings; /* [n_grid]           */
+} McsThermoIn;
+/* out arrays [n_grid] each (NULL = skip): P_psd_par, P_psd_perp, energy_density_psd as returned by thermo_calcs, and the
+ * normalised zone totals d2N_pop (:225).  The CR re-binning adds FP64 cells with atomics: sums agree with the serial order
+ * to rounding (~1e-15 relative), not bit for bit. */
+MCS_API int mcs_thermo(McsHandle* h, const McsThermoIn* in, double* P_psd_par, double* P_psd_perp, double* energy_density_psd,
+                       double* d2N_pop);
+
 /* Inspection (tests, host-side new_pcut, replay parity). `which`: 0 = current population (*_new),
  * 1 = *_saved arrays of the last pcut (sparse, with l_save). n = number of entries to copy. */
 MCS_API int mcs_get_population(McsHandle* h, int32_t which, int64_t n, McsPopulation* out, uint8_t* l_save);

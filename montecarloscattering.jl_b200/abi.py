@@ -122,8 +122,13 @@ ABI_SYMBOLS = (
     "mcs_comm_unique_id", "mcs_comm_init", "mcs_set_profile", "mcs_begin_ion", "mcs_begin_ion_generate", "mcs_run_pcut", "mcs_split", "mcs_split_explicit",
     "mcs_run_ion", "mcs_end_ion", "mcs_get_population", "mcs_population_size", "mcs_get_fates",
     "mcs_replay_set_stream", "mcs_trace_enable", "mcs_trace_get", "mcs_get_timing", "mcs_measure_fp64_peak",
-    "mcs_measure_atomic_peak", "mcs_measure_scatter_peak", "mcs_selftest_math",
+    "mcs_measure_atomic_peak", "mcs_measure_scatter_peak", "mcs_selftest_math", "mcs_thermo",
 )
+
+
+class McsThermoIn(C.Structure):
+    _fields_ = [("cos_center", _pd), ("pt_center", _pd), ("zone_pop", _pd), ("temperature_K", _d),
+                ("psd", _pd), ("therm_d2N_pf", _pd), ("num_crossings", _pi64)]
 
 
 class McsError(RuntimeError):
@@ -168,6 +173,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.mcs_measure_atomic_peak.argtypes = [H, _i64, _pd]
     lib.mcs_measure_scatter_peak.argtypes = [H, _pd]
     lib.mcs_selftest_math.argtypes = [H, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.mcs_thermo.argtypes = [H, C.POINTER(McsThermoIn), _pd, _pd, _pd, _pd]
     sizes = (_i32 * 6)()
     lib.mcs_abi_sizes(C.byref(sizes))
     want = [C.sizeof(t) for t in (McsConfig, McsSpecies, McsTallies, McsPopulation, McsTraceRec, McsTiming)]
@@ -365,6 +371,27 @@ class Engine:
                                                     "n_errors")}
         t.stats["n_fate"] = [int(v) for v in st.n_fate]
         return t
+
+    def thermo(self, cos_center, pt_center, zone_pop, temperature_K: float, psd=None, therm_d2N_pf=None, num_crossings=None):
+        """thermo_calcs on the tallies of the ion just ended (or on the three host arrays, given together):
+        returns (P_psd_par, P_psd_perp, energy_density_psd, d2N_pop), [n_grid] each."""
+        ng = self.n_grid
+        f = lambda a, n: np.ascontiguousarray(a, dtype=np.float64).reshape(-1)[:n] if a is not None else None
+        keep = [f(cos_center, self.T + 1), f(pt_center, self.M + 1), f(zone_pop, ng), f(psd, None), f(therm_d2N_pf, None),
+                np.ascontiguousarray(num_crossings, dtype=np.int64) if num_crossings is not None else None]
+        if len(keep[0]) != self.T + 1 or len(keep[1]) != self.M + 1 or len(keep[2]) != ng:
+            raise McsError("thermo: cos_center [T+1], pt_center [M+1], zone_pop [n_grid]")
+        n_psd = ng * (self.M + 2) * (self.T + 2)
+        for a in keep[3:5]:
+            if a is not None and a.size != n_psd:
+                raise McsError("thermo: psd / therm_d2N_pf must hold (M+2)(T+2)n_grid cells")
+        if keep[5] is not None and keep[5].size != ng:
+            raise McsError("thermo: num_crossings [n_grid]")
+        tin = McsThermoIn(_ptr(keep[0], _pd), _ptr(keep[1], _pd), _ptr(keep[2], _pd), float(temperature_K),
+                          _ptr(keep[3], _pd), _ptr(keep[4], _pd), _ptr(keep[5], _pi64))
+        out = [np.zeros(ng) for _ in range(4)]
+        self._check(self.lib.mcs_thermo(self._h, C.byref(tin), *[_ptr(o, _pd) for o in out]))
+        return tuple(out)
 
     def population_size(self) -> int:
         return int(self.lib.mcs_population_size(self._h))

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "mcs_device.cuh"
+#include "mcs_thermo.cuh"
 
 using namespace mcs;
 
@@ -141,6 +142,7 @@ struct McsHandle {
     unsigned char* d_xchg = nullptr;  // all-gather buffer of saved records for the rebalancing split
     size_t xchg_bytes = 0;
     bool reduced = false;             // mcs_end_ion already summed the tallies over ranks (idempotence)
+    bool ended = false;               // mcs_end_ion has folded the accumulators: d_tally holds this ion's final FP64 tallies
     bool split_timed = false;         // ev2/ev3 bracket an un-timed split (elapsed time read at the next sync)
     unsigned long long steps0 = 0, saved0 = 0, reds0 = 0;  // counter values before the pcut in flight
     McsTiming tm;
@@ -411,7 +413,7 @@ extern "C" int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const 
         if (pop->grid[i] < 0 || pop->grid[i] > h->ng + 1) return fail(MCS_ERR_ARG, "grid index out of range");
     { int rcg = check_index_range(first_global, n); if (rcg) return rcg; }
     CU(cudaSetDevice(h->device));
-    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->split_timed = false;
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->ended = false; h->split_timed = false;
     h->n_use = n; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     // clear_psd! (ion_init.jl:1-16) and every other per-ion sum
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
@@ -457,7 +459,7 @@ extern "C" int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_io
     { int rcg = check_index_range(first_global, n_local); if (rcg) return rcg; }
     if (n_total > 0x100000000ll) return fail(MCS_ERR_ARG, "global particle index exceeds 2^32 (RNG counter width)");
     CU(cudaSetDevice(h->device));
-    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->split_timed = false;
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->ended = false; h->split_timed = false;
     h->n_use = n_local; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
     if (h->d_acc) CU(cudaMemsetAsync(h->d_acc, 0, h->n_tally * ACC_D * 8, h->stream));
@@ -891,6 +893,55 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     t->n_warn_pperp = (int64_t)c[CNT_W_PPERP]; t->n_warn_psd_mom = (int64_t)c[CNT_W_PSDMOM]; t->n_neg_sqrt = (int64_t)c[CNT_NEGSQRT];
     t->n_retro_capped = (int64_t)c[CNT_RETRO_CAP]; t->n_errors = (int64_t)c[CNT_ERR];
     for (int i = 0; i < 6; i++) t->n_fate[i] = (int64_t)c[CNT_FATE0 + i];
+    h->ended = true;
+    return MCS_OK;
+}
+
+// thermo_calcs.jl:31-355 on the tallies where they lie (kernel in mcs_thermo.cuh)
+extern "C" int mcs_thermo(McsHandle* h, const McsThermoIn* in, double* P_par, double* P_perp, double* e_dens, double* d2N_pop) {
+    if (!h || !in || !in->cos_center || !in->pt_center || !in->zone_pop) return fail(MCS_ERR_ARG, "null argument");
+    if (!h->cfg.bin_thermal) return fail(MCS_ERR_ARG, "mcs_thermo needs cfg.bin_thermal = 1");
+    if (!h->have_profile) return fail(MCS_ERR_STATE, "mcs_set_profile first");
+    const bool resident = !(in->psd && in->therm_d2N_pf && in->num_crossings);
+    if (resident && (in->psd || in->therm_d2N_pf || in->num_crossings))
+        return fail(MCS_ERR_ARG, "give psd, therm_d2N_pf and num_crossings together or none of them");
+    if (resident && !h->ended) return fail(MCS_ERR_STATE, "mcs_end_ion first: the tallies are not folded / summed over ranks yet");
+    CU(cudaSetDevice(h->device));
+    const size_t ng = (size_t)h->ng, np = psd_len(h), nT = (size_t)h->T + 1, nM = (size_t)h->M + 1;
+    // one scratch allocation: slab | cos | pt | zone_pop | 4 outputs | [psd | therm | ncross]
+    const size_t n_d = np + nT + nM + ng + 4 * ng + (resident ? 0 : 2 * np + ng);
+    double* d = nullptr;
+    CU(cudaMalloc(&d, n_d * 8));
+    double *slab = d, *d_cos = slab + np, *d_pt = d_cos + nT, *d_zp = d_pt + nM, *d_out = d_zp + ng, *d_in = d_out + 4 * ng;
+    cudaError_t e = cudaSuccess;
+#define UP(dst, src, count) if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, (size_t)(count) * 8, cudaMemcpyHostToDevice, h->stream)
+    UP(d_cos, in->cos_center, nT); UP(d_pt, in->pt_center, nM); UP(d_zp, in->zone_pop, ng);
+    if (!resident) { UP(d_in, in->psd, np); UP(d_in + np, in->therm_d2N_pf, np); UP(d_in + 2 * np, in->num_crossings, ng); }
+#undef UP
+    ThermoParams P;
+    P.ng = h->ng; P.T = h->T; P.M = h->M;
+    P.c = h->cfg.c_cms; P.m = h->sp.aa * h->cfg.mp_g; P.n0 = h->sp.n0; P.gam0 = h->cfg.gam0; P.beta0 = h->cfg.beta0;
+    P.temperature_K = in->temperature_K;
+    P.psd_mom_min = h->P.psd_mom_min; P.bpd_mom = h->P.bpd_mom; P.psd_cos_fine = h->P.psd_cos_fine; P.delta_cos = h->P.delta_cos;
+    P.psd_theta_min = h->P.psd_theta_min; P.bpd_th = h->P.bpd_th;
+    P.gsf = h->P.gsf; P.ux = h->P.ux;
+    P.cos_center = d_cos; P.pt_center = d_pt; P.zone_pop = d_zp;
+    P.psd = resident ? h->d_tally + h->off_psd : d_in;
+    P.therm_pf = resident ? h->d_tally + h->off_thpf : d_in + np;
+    P.ncross = resident ? h->d_u64 : (const unsigned long long*)(d_in + 2 * np);
+    P.slab = slab;
+    P.P_par = d_out; P.P_perp = d_out + ng; P.e_dens = d_out + 2 * ng; P.pop = d_out + 3 * ng;
+    if (e == cudaSuccess) {
+        thermo_kernel<<<(unsigned)h->ng, 256, 0, h->stream>>>(P);
+        e = cudaGetLastError();
+        h->tm.other_launches++;
+    }
+#define DN(dst, k) if (e == cudaSuccess && dst) e = cudaMemcpyAsync(dst, d_out + (k) * ng, ng * 8, cudaMemcpyDeviceToHost, h->stream)
+    DN(P_par, 0); DN(P_perp, 1); DN(e_dens, 2); DN(d2N_pop, 3);
+#undef DN
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(MCS_ERR_CUDA, "mcs_thermo: %s", cudaGetErrorString(e));
     return MCS_OK;
 }
 

@@ -826,3 +826,71 @@ def synthetic_precursor(run: Run, r_sub: float = 3.0, scale_rg: float = 5.0) -> 
         bt = np.sqrt(np.abs(8 * math.pi * p.epsB * ed))
     return Profile(x_grid_rg=p.x_grid_rg.copy(), x_grid_cm=p.x_grid_cm.copy(), ux_sk=ux, uz_sk=np.zeros(n), utot=ux.copy(),
                    gam_sf=gsf, gam_ef=gef, beta_ef=bef, btot=bt, theta=p.theta.copy(), epsB=p.epsB.copy())
+
+
+# ------------------------------------------------------------------------------------------------
+# Inputs of the pressure consumer: bin centres and zone populations, host side as in the reference
+def psd_bounds(run: Run, as_written: bool = True):
+    """(psd_mom_bounds [0..M+1], psd_theta_bounds [0..T+1]) of set_psd_mom_bins / set_psd_angle_bins
+    (/root/reference/src/initializers.jl:216-285).
+
+    as_written: the reference ends set_psd_angle_bins with `sort!(psd_theta_bounds)`, which interleaves the angle part
+    (radians, ascending) with the cosine part (descending from psd_cos_fine to -1) — the docstring above it promises the
+    unsorted order.  False returns that intended order."""
+    bpd_p, bpd_t = run.inp.num_psd_bins_per_decade
+    M = run.num_psd_mom_bins
+    log_p_min = math.log10(run.psd_mom_min / (MP * CL))
+    mom = np.concatenate(([-99.0], log_p_min + np.arange(M + 1) / bpd_p))
+    lin = run.inp.psd_linear_cosine_bins
+    n_log = run.num_psd_theta_bins - lin
+    root = 10.0 ** (1.0 / bpd_t)
+    th = np.concatenate(([1.0e-99], run.psd_theta_min * root ** np.arange(n_log), run.psd_cos_fine - run.delta_cos * np.arange(lin + 1)))
+    if as_written:
+        th = np.sort(th)
+    return mom, th
+
+
+def thermo_inputs(run: Run, prof: Profile, i_ion: int, jet_rad_pc: float = 0.438, jet_open_ang_deg: float = 5.0,
+                  as_written: bool = False):
+    """(cos_center [T+1], pt_center [M+1], zone_pop [n_grid]) for `mcs_thermo`.
+
+    cos_center / pt_center follow thermo_calcs.jl:55-82, zone_pop follows set_grid_volumes!
+    (particle_counter.jl:1463-1523; jet radius / opening angle default to the bundled mc_in.toml:192-195).
+    as_written keeps two quirks of the reference: the sorted theta bounds (see psd_bounds) and
+    `pt_center = exp10(log_p_mid) g cm/s`, although psd_mom_bounds holds log10(p / m_p c) — i.e. momenta too large by
+    1/(m_p c).  The default (False) uses the unsorted bounds and multiplies by m_p c, which is what the re-binning against
+    psd_mom_min [g cm/s] needs to land inside the grid."""
+    mom, th = psd_bounds(run, as_written=as_written)
+    T, M, lin = run.num_psd_theta_bins, run.num_psd_mom_bins, run.inp.psd_linear_cosine_bins
+    cosc = np.zeros(T + 1)
+    for j in range(T + 1):
+        if j > T - lin:
+            hi, lo = th[j], th[j + 1]
+        elif j == T - lin:
+            hi, lo = math.cos(th[j]), th[j + 1]
+        else:
+            hi, lo = math.cos(th[j]), math.cos(th[j + 1])
+        cosc[j] = -(lo + hi) / 2
+    ptc = 10.0 ** ((mom[:-1] + mom[1:]) / 2)
+    if not as_written:
+        ptc = ptc * (MP * CL)
+    # set_grid_volumes!
+    ng, ish, g0 = run.n_grid, run.i_shock, run.gam0
+    xg = np.asarray(prof.x_grid_cm, float)
+    dx = np.diff(xg)                       # dx[i] = x[i+1] - x[i], zone i = 1..n_grid
+    sph = (1 - math.cos(math.radians(jet_open_ang_deg))) / 2   # parse_jet_frac, data_input.jl:158-166
+    rad_cm = jet_rad_pc * PC_CM
+    area = np.zeros(ng + 1)
+    r_min = rad_cm - xg[ish]
+    for i in range(ish - 1, 0, -1):
+        r_max = r_min + dx[i] / g0
+        area[i] = math.pi * (r_max + r_min) ** 2 * sph
+        r_min = r_max
+    r_max = rad_cm - xg[ish]
+    for i in range(ish, ng + 1):
+        r_min = r_max - dx[i] / g0
+        area[i] = math.pi * (r_max + r_min) ** 2 * sph
+        r_max = r_min
+    F_up = g0 * run.species[i_ion].n0 * run.beta0 * CL
+    zone_pop = np.array([F_up * area[i] * dx[i] / float(prof.ux_sk[i]) for i in range(1, ng + 1)])
+    return cosc, ptc, zone_pop

@@ -78,7 +78,7 @@ static void pop_zero(Pop* p, int64_t n) {
 struct McsHandle {
     McsConfig cfg;
     McsSpecies sp;
-    int have_profile, have_ion;
+    int have_profile, have_ion, ended;
     int32_t i_iter, i_ion, i_pcut;
     double pcut, pcut_prev;
     int n_grid, M, T; /* zones, num_psd_mom_bins, num_psd_theta_bins */
@@ -936,7 +936,7 @@ int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies*
         P->tcut[i] = pop->tcut ? pop->tcut[i] : 1;
         if (P->grid[i] < 0 || P->grid[i] > h->n_grid + 1) return fail(MCS_ERR_ARG, "grid index out of range");
     }
-    h->have_ion = 1;
+    h->have_ion = 1; h->ended = 0;
     return MCS_OK;
 }
 
@@ -986,7 +986,7 @@ int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_ion, const Mc
         P->down[i] = 0; P->inj[i] = 0; P->xn_per[i] = h->cfg.xn_per_fine; P->prp_x[i] = h->cfg.x_grid_stop;
         P->acctime[i] = 0.0; P->tcut[i] = 1;
     }
-    h->have_ion = 1;
+    h->have_ion = 1; h->ended = 0;
     return MCS_OK;
 }
 
@@ -1108,6 +1108,92 @@ int mcs_end_ion(McsHandle* h, McsTallies* t) {
     t->n_warn_pperp = h->w_pperp; t->n_warn_psd_mom = h->w_psdmom; t->n_neg_sqrt = h->n_negsqrt;
     t->n_retro_capped = h->n_retro_cap; t->n_errors = h->n_err;
     memcpy(t->n_fate, h->n_fate, sizeof t->n_fate);
+    h->ended = 1;
+    return MCS_OK;
+}
+
+/* thermo_calcs.jl:31-355 on the binned tallies.  The thermal log of the reference (:96-164) is replaced by
+ * th_pf, the same crossings binned as they happen (see all_flux above, which applies :143-160 per crossing). */
+int mcs_thermo(McsHandle* h, const McsThermoIn* in, double* P_par, double* P_perp, double* e_dens, double* d2N_pop_out) {
+    if (!h || !in || !in->cos_center || !in->pt_center || !in->zone_pop) return fail(MCS_ERR_ARG, "null argument");
+    if (!h->cfg.bin_thermal) return fail(MCS_ERR_ARG, "mcs_thermo needs cfg.bin_thermal = 1");
+    if (!h->have_profile) return fail(MCS_ERR_STATE, "mcs_set_profile first");
+    const int resident = !(in->psd && in->therm_d2N_pf && in->num_crossings);
+    if (resident && (in->psd || in->therm_d2N_pf || in->num_crossings))
+        return fail(MCS_ERR_ARG, "give psd, therm_d2N_pf and num_crossings together or none of them");
+    if (resident && !h->ended) return fail(MCS_ERR_STATE, "mcs_end_ion first: the tallies are not folded / summed over ranks yet");
+    const McsConfig* c = &h->cfg;
+    const int ng = h->n_grid, T2 = h->T + 2, M2 = h->M + 2;
+    const size_t slab = (size_t)T2 * (size_t)M2;
+    const double* psd = in->psd ? in->psd : h->psd;
+    const double* thp = in->therm_d2N_pf ? in->therm_d2N_pf : h->th_pf;
+    const int64_t* ncr = in->num_crossings ? in->num_crossings : h->ncross;
+    const double cl = c->c_cms, m = h->sp.aa * c->mp_g, mc = m * cl, E0 = m * (cl * cl); /* :53 */
+    const double kB = 1.380649e-16; /* Unitful k, erg/K */
+    double* d2N = malloc(slab * 8);
+    if (!d2N) return fail(MCS_ERR_NOMEM, "out of memory");
+    for (int i = 1; i <= ng; i++) {
+        const double g = h->gsf[i], b = h->ux[i] / cl;
+        for (size_t q = 0; q < slab; q++) d2N[q] = 1.0e-99 + thp[q + slab * (size_t)(i - 1)]; /* :43, :133-164 */
+        /* :178-207 — CR cells re-binned by the boost of their centre */
+        for (int jt = 0; jt <= h->T; jt++)
+            for (int k = 0; k <= h->M; k++) {
+                double cell = psd[(size_t)k + (size_t)M2 * ((size_t)jt + (size_t)T2 * (size_t)(i - 1))];
+                if (cell <= 1.0e-66) continue;
+                double pt = in->pt_center[k], px = pt * in->cos_center[jt];
+                double etot = hypot(pt * cl, E0);
+                double pxX = g * (px - b * etot / cl);
+                double ptX = sqrt(pt * pt - px * px + pxX * pxX);
+                int kX = get_psd_bin_momentum(h, ptX), jX = get_psd_bin_angle(h, pxX, ptX);
+                d2N[(size_t)jX + (size_t)T2 * (size_t)kX] += cell;
+            }
+        /* :209-226 — normalise to the zone population */
+        double nf = 0.0;
+        for (size_t q = 0; q < slab; q++) if (d2N[q] > 1.0e-66) nf += d2N[q];
+        if (ncr[i - 1] == 0 && nf > 0) nf += h->sp.n0 / h->ux[i];
+        if (nf > 0) nf = in->zone_pop[i - 1] / nf;
+        double pop = 0.0;
+        for (size_t q = 0; q < slab; q++) if (d2N[q] > 1.0e-66) { d2N[q] *= nf; }
+        for (size_t q = 0; q < slab; q++) if (d2N[q] > 1.0e-66) pop += d2N[q];
+        if (d2N_pop_out) d2N_pop_out[i - 1] = pop;
+        /* :242-352 — the three normalisation cases, then the sums */
+        double dmax = 0.0;
+        for (size_t q = 0; q < slab; q++) if (d2N[q] > dmax) dmax = d2N[q];
+        const double dens = c->gam0 * c->beta0 * h->sp.n0 / sqrt(g * g - 1.0);
+        double par = 0.0, perp = 0.0, en = 0.0, norm = 0.0;
+        int sum_cells = 1;
+        if (dmax < 1.0e-66 && ncr[i - 1] == 0) { /* (1) nothing detected: cold thermal gas, Gamma = 5/3 */
+            double pl = pow(dens, 5.0 / 3.0) * kB * in->temperature_K;
+            par += 1.0 / 3.0 * pl; perp += 2.0 / 3.0 * pl; en += 1.5 * pl;
+            sum_cells = 0;
+        } else if (ncr[i - 1] == 0) { /* (2) CRs only */
+            double pl = pow(dens, 5.0 / 3.0) * kB * in->temperature_K;
+            pl *= 1.0 - pop / in->zone_pop[i - 1];
+            par += 1.0 / 3.0 * pl; perp += 2.0 / 3.0 * pl;
+            norm = dens / in->zone_pop[i - 1];
+            en += 1.5 * pl;
+        } else { /* (3) thermal crossings seen: d2N is the whole population */
+            norm = dens / in->zone_pop[i - 1];
+        }
+        if (sum_cells)
+            for (int k = 0; k <= h->M; k++) {
+                double pt = in->pt_center[k];
+                double gt = hypot(1.0, pt / mc);
+                double vel = pt * cl / (mc * gt); /* :236 */
+                double pf = 1.0 / 3.0 * pt * vel * norm, ef = (gt - 1.0) * E0;
+                for (int jt = 0; jt <= h->T; jt++) {
+                    double d = d2N[(size_t)jt + (size_t)T2 * (size_t)k];
+                    if (d < 1.0e-66) continue;
+                    double c2 = in->cos_center[jt] * in->cos_center[jt];
+                    par += d * pf * c2; perp += d * pf * (1.0 - c2);
+                    en += ef * d * norm;
+                }
+            }
+        if (P_par) P_par[i - 1] = par;
+        if (P_perp) P_perp[i - 1] = perp;
+        if (e_dens) e_dens[i - 1] = en;
+    }
+    free(d2N);
     return MCS_OK;
 }
 

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpur
 if [ -z "$SKIP_TESTS" ]; then
   # TEST_LIB=variant runs the parity tests on that build instead of the default library
   TL=""; [ -n "$TEST_LIB" ] && TL=$PWD/montecarloscattering.jl_b200/libmcs_b200_$TEST_LIB.so
-  MCS_LIB=$TL timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > gpurun_out/${TAG}_pytest.log 2>&1
+  MCS_LIB=$TL timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/${TAG}_pytest.log 2>&1
   echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log
 fi
 for w in $WORKLOADS; do
