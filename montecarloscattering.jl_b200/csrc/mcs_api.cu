@@ -885,9 +885,8 @@ extern "C" int mcs_end_ion(McsHandle* h, McsTallies* t) {
     {
         fprintf(stderr, "[mcs] lane-passes: fast %llu general %llu | warp iterations: fast %llu general %llu\n", c[CNT_FAST_LANE],
                 c[CNT_SLOW_LANE], c[CNT_FAST_ITER], c[CNT_SLOW_SEC]);
-        fprintf(stderr, "[mcs] park reasons: cap %llu ret1 %llu psp %llu pmax %llu feb %llu pcut %llu other-pre %llu | shock %llu inj %llu stop %llu prp %llu beyond %llu reflect %llu other-post %llu\n",
-                c[CNT_PARK0], c[CNT_PARK0 + 1], c[CNT_PARK0 + 2], c[CNT_PARK0 + 3], c[CNT_PARK0 + 4], c[CNT_PARK0 + 5], c[CNT_PARK0 + 6],
-                c[CNT_PARK0 + 8], c[CNT_PARK0 + 9], c[CNT_PARK0 + 10], c[CNT_PARK0 + 11], c[CNT_PARK0 + 12], c[CNT_PARK0 + 13], c[CNT_PARK0 + 14]);
+        fprintf(stderr, "[mcs] lane-iterations not spent on a pass: waiting for the general section %llu, without a particle %llu, waiting for a boost %llu\n",
+                c[CNT_PARK0], c[CNT_PARK0 + 1], c[CNT_PARK0 + 2]);
     }
     t->n_helix_steps = (int64_t)c[CNT_HELIX]; t->n_retro_steps = (int64_t)c[CNT_RETRO];
     t->n_warn_pperp = (int64_t)c[CNT_W_PPERP]; t->n_warn_psd_mom = (int64_t)c[CNT_W_PSDMOM]; t->n_neg_sqrt = (int64_t)c[CNT_NEGSQRT];

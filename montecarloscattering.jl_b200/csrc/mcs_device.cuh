@@ -167,20 +167,20 @@ struct DevParams {
 // Shared memory of one block: [zone table | warp 0 region | warp 1 region | ...].
 //  zone table (fast loop): per grid node i = 0..ng+1 three 16-byte pairs {ux, gsf}, {gef, cos th}, {xg[i], xg[i+1]} and the gyro
 //  denominator 1/(zz*btot[i]); a pass reads its zone's constants from here instead of holding them in registers.
-//  warp region: flux partials pxx | pxz | efl (ng each) | scalars (SC_N), then the event queue (QCAP x 64 B, SoA).
+//  warp region: flux partials pxx | pxz | efl (ng each) | scalars (SC_N), then the event queue (QCAP x 72 B, SoA).
 //  azimuth table (fast loop): 256 x {sin, cos} of the bin centres of the scattering azimuth (see az_sincos).
 constexpr int AZ_N = 256;
 __host__ __device__ inline size_t zone_tab_bytes(int ng) { return ((((size_t)(ng + 2) * 56) + 15) & ~(size_t)15) + (size_t)AZ_N * 16; }
 __host__ __device__ inline size_t warp_smem_bytes(int ng) {
-    return (size_t)(3 * ng + SC_N) * 8 + (size_t)QCAP * (7 * 8 + 4 * 4);
+    return (size_t)(3 * ng + SC_N) * 8 + (size_t)QCAP * (6 * 8 + 6 * 4);
 }
 __host__ __device__ inline size_t block_smem_bytes(int ng, int warps) { return zone_tab_bytes(ng) + (size_t)warps * warp_smem_bytes(ng); }
 
 // per-warp shared-memory view
 struct WarpMem {
     double* part;  // [3*ng + SC_N]: pxx | pxz | efl | scalars
-    double *q_pb, *q_pperp, *q_gam, *q_cphi, *q_sphi, *q_w, *q_ptot;  // the gyro-phase travels as (cos, sin)
-    int *q_inew, *q_iold, *q_iz;
+    double *q_pb, *q_pperp, *q_gam, *q_cphi, *q_sphi, *q_ptot;  // the gyro-phase travels as (cos, sin)
+    int *q_inew, *q_iold, *q_iz, *q_ip;  // q_ip: particle index (its weight is read when the queue is drained)
     uint32_t* q_flags;
 };
 
@@ -193,10 +193,10 @@ __device__ __forceinline__ WarpMem warp_mem(int warp, int ng) {
     w.part = reinterpret_cast<double*>(p);
     double* q = w.part + 3 * ng + SC_N;
     w.q_pb = q; w.q_pperp = q + QCAP; w.q_gam = q + 2 * QCAP; w.q_cphi = q + 3 * QCAP; w.q_sphi = q + 4 * QCAP;
-    w.q_w = q + 5 * QCAP; w.q_ptot = q + 6 * QCAP;
-    int* qi = reinterpret_cast<int*>(q + 7 * QCAP);
-    w.q_inew = qi; w.q_iold = qi + QCAP; w.q_iz = qi + 2 * QCAP;
-    w.q_flags = reinterpret_cast<uint32_t*>(qi + 3 * QCAP);
+    w.q_ptot = q + 5 * QCAP;
+    int* qi = reinterpret_cast<int*>(q + 6 * QCAP);
+    w.q_inew = qi; w.q_iold = qi + QCAP; w.q_iz = qi + 2 * QCAP; w.q_ip = qi + 3 * QCAP;
+    w.q_flags = reinterpret_cast<uint32_t*>(qi + 4 * QCAP);  // (+ one spare int column keeps the region a multiple of 8 bytes)
     return w;
 }
 struct ZoneTab { const double2 *a, *b, *c; const double* gd; const double2* az; };  // {ux, gsf} | {gef, cos th} | {xg[i], xg[i+1]} | 1/(zz*btot) | azimuth
@@ -683,8 +683,9 @@ __device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) 
     const bool act = lane < n_ev;
     const int q = base + (act ? lane : 0);
     const uint32_t fl = act ? wm.q_flags[q] : 0u;
+    const double weight = act ? P.cur.weight[wm.q_ip[q]] : 0.0;
     const double pb = wm.q_pb[q], pperp = wm.q_pperp[q], gam_pf = wm.q_gam[q], cphi = wm.q_cphi[q], sphi = wm.q_sphi[q],
-                 weight = wm.q_w[q], ptot = wm.q_ptot[q];
+                 ptot = wm.q_ptot[q];
     const int i_new = wm.q_inew[q], i_old = wm.q_iold[q], iz = wm.q_iz[q];
     const double ux = P.ux[iz], gsf = P.gsf[iz], bcos = P.costh[iz], bsin = P.sinth[iz];
     double ptot_sk, sx, sz, gam_sk;
@@ -987,7 +988,7 @@ __device__ __forceinline__ int push_events(const DevParams& P, const WarpMem& wm
         if (ev) {
             const int q = qn + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
             wm.q_pb[q] = pb; wm.q_pperp[q] = pperp; wm.q_gam[q] = gam_pf; wm.q_cphi[q] = cphi; wm.q_sphi[q] = sphi;
-            wm.q_w[q] = P.cur.weight[ip];
+            wm.q_ip[q] = ip;  // the weight is fetched when the queue is drained (32 lanes at once)
             wm.q_ptot[q] = ptot; wm.q_inew[q] = i_new; wm.q_iold[q] = i_old; wm.q_iz[q] = iz; wm.q_flags[q] = ev;
         }
         qn += cnt;
@@ -1442,7 +1443,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
     L.rng_exhausted = false; L.queue_empty = false; L.down = false; L.inj = false; L.x_old_le0 = true; L.parked = true;
     L.mu = 0; L.sn = 1; L.cph = 1; L.sph = 0; L.cs_valid = false; L.cs_flags = 0u;
 #ifdef MCS_SCHED_COUNTERS
-    unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_sections = 0;
+    unsigned long long c_fast_lane = 0, c_fast_iter = 0, c_sections = 0, c_wait = 0, c_idle = 0, c_psp = 0;
 #define MCS_SC(x) x
 #else
 #define MCS_SC(x)
@@ -1571,24 +1572,30 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         // Is this a plain pass?  Same zone, and inside the grid or between its end and the PRP.
                         const bool dn = x_n > x;
                         const bool same = dn ? (zc.y > x_n) : (zc.x <= x_n);
-                        bool rare = !same | !(sn2 > 0.0) | park |
-                                    ((x_n >= P.x_grid_stop) & ((x < P.x_grid_stop) | (x_n >= prp_x) | ELECTRON));
-                        if (st & ST_INJ) rare |= x_n < P.feb_up;
-                        if (P.feb_dn > 0) rare |= x_n > P.feb_dn;
-                        if (reflect_cfg) rare |= (x_n <= 0) & (x > 0);
+                        // `other`: anything but a zone change inside the grid (also a NaN position: !(NaN < stop))
+                        const bool beyond = !(x_n < P.x_grid_stop);
+                        bool other = !(sn2 > 0.0) | park | (beyond & ((x < P.x_grid_stop) | !(x_n < prp_x) | ELECTRON));
+                        if (st & ST_INJ) other |= x_n < P.feb_up;
+                        if (P.feb_dn > 0) other |= x_n > P.feb_dn;
+                        if (reflect_cfg) other |= (x_n <= 0) & (x > 0);
                         int ig_new = iz;
                         double prp_n = prp_x;
                         uint32_t st_n = st;
                         bool go = true;
-                        if (rare) {
-                            // anything the general pass would have to act on after the move -> nothing is committed
-                            bool pk = park | !(sn2 > 0.0) | !(x_n == x_n) | (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) |
-                                      (P.feb_dn > 0 && x_n > P.feb_dn);
+                        if (other | !same) {
+                            // Runs in every other iteration of a warp (one lane or two): most often a zone boundary crossed
+                            // inside the grid and nothing else, so everything else nests under `other`.
+                            bool pk = false;
                             const bool cross_down = x < 0 && x_n >= 0;
                             if (cross_down) {  // particle_loop.jl:413-429: arrival downstream, make the region long enough
                                 const double Ld = P.eta_mfp / 3 * grt * L.ptot / (P.m * L.gam_pf * P.u2);
                                 prp_n = fmax(prp_x, Ld);
                             }
+                            if (other) {
+                            // anything the general pass would have to act on after the move -> nothing is committed
+                            pk = park | !(sn2 > 0.0) | !(x_n == x_n) | (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) |
+                                 (P.feb_dn > 0 && x_n > P.feb_dn);
+                            // (not `other`: x_n < x_grid_stop <= prp_x, or x_grid_stop <= x, x_n < prp_x — neither test below fires)
                             if (x_n > 1.1 * prp_n) {
                                 // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes beyond 6.91 L_diff
                                 double v_fac;
@@ -1605,11 +1612,13 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                                     pk |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
                                 }
                             }
+                            }
                             if (!pk) {
                                 // zone search (all_flux.jl:65-82) and the crossing event
                                 if (!same) {
-                                    if (dn) { int k = iz + 1; while (k <= ng + 1 && !(P.xg[k] > x_n)) k++; ig_new = k - 1; }
-                                    else { int k = iz; while (k >= 0 && !(P.xg[k] <= x_n)) k--; ig_new = k; }
+                                    // on the shared table {xg[j], xg[j+1]}, starting at the neighbour (the own zone is excluded)
+                                    if (dn) { int j = iz + 1; while (j <= ng && !(zt.c[j].y > x_n)) j++; ig_new = j; }
+                                    else { int j = iz - 1; while (j >= 0 && !(zt.c[j].x <= x_n)) j--; ig_new = j; }
                                 }
                                 if (cross_down) st_n |= ST_DOWN;
                                 if ((st_n & ST_DOWN) && x_n < 0) st_n |= ST_INJ;  // particle_loop.jl:433-435 (before all_flux)
@@ -1648,6 +1657,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                 // refills), or the bound on consecutive iterations is reached
                 MCS_SC(c_fast_iter++;)
                 const int n_wait = __popc(__ballot_sync(FULL, ip >= 0 && (st & ST_PARKED)));
+                MCS_SC(c_wait += n_wait; c_idle += __popc(__ballot_sync(FULL, ip < 0)); c_psp += __popc(__ballot_sync(FULL, (st & ST_NEEDPSP) != 0u));)
                 wait_debt += n_wait;
                 const bool leaving = (n_wait > 0 && n_wait >= park_t) || (MCS_WAIT_DEBT > 0 && wait_debt >= MCS_WAIT_DEBT) ||
                                      it == MCS_FAST_MAX - 1;
@@ -1734,7 +1744,8 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
     if (L.qn > 0) process_events(P, 0, L.qn);
 
     MCS_SC(count(P, CNT_FAST_LANE, c_fast_lane);
-           if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_sections); })
+           if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_sections);
+                            count(P, CNT_PARK0, c_wait); count(P, CNT_PARK0 + 1, c_idle); count(P, CNT_PARK0 + 2, c_psp); })
     // ---- block partials -------------------------------------------------------------------------------
     __syncthreads();
     const int np = 3 * ng + SC_N;

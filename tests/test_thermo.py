@@ -104,7 +104,7 @@ def _case(cfg):
 def test_oracle_thermo_equals_restatement(olib, cfg):
     run, prof = _case(cfg)
     sp = run.species[0]
-    e, t = _ion_tallies(olib, run, prof=prof)
+    e, t = _ion_tallies(olib, run, n_cut=8 if cfg == "relativistic" else 4, prof=prof)
     cosc, ptc, zp = problem.thermo_inputs(run, prof, 0)
     got = np.array(e.thermo(cosc, ptc, zp, sp.T))
     want = thermo_restated(run, prof, sp, cosc, ptc, zp, sp.T, t.psd, t.therm_d2N_pf, t.num_crossings)
@@ -213,8 +213,9 @@ def test_thermo_inputs_follow_reference_bin_centres():
 def test_device_thermo_matches_oracle(olib, clib, cfg):
     run, prof = _case(cfg)
     sp = run.species[0]
-    eo, to = _ion_tallies(olib, run, prof=prof)
-    ec, tc = _ion_tallies(clib, run, prof=prof)
+    n_cut = 8 if cfg == "relativistic" else 4      # the first cosmic rays of the gamma0 = 10 ladder appear at pcut 5
+    eo, to = _ion_tallies(olib, run, n_cut=n_cut, prof=prof)
+    ec, tc = _ion_tallies(clib, run, n_cut=n_cut, prof=prof)
     cosc, ptc, zp = problem.thermo_inputs(run, prof, 0)
     want = np.array(eo.thermo(cosc, ptc, zp, sp.T))
     # (a) identical inputs: only the order of the FP64 adds differs
@@ -224,8 +225,10 @@ def test_device_thermo_matches_oracle(olib, clib, cfg):
     assert (to.num_crossings > 0).sum() > 10 and (to.psd > 0).sum() > 100
     for k, nm in enumerate(("P_psd_par", "P_psd_perp", "energy_density_psd", "d2N_pop")):
         assert np.all(np.isfinite(same_in[k])), nm
-        assert rel_close(same_in[k], want[k], 0) < 1e-12, nm
-        assert rel_close(resident[k], want[k], 0) < 1e-9, nm
+        # energy_density sums (hypot(1, p/mc) - 1) E0: for p/mc ~ 1e-3 one ulp of the device hypot against glibc's is
+        # 1e-16 / 5e-7 of the term — the reference's own formula is that ill-conditioned
+        assert rel_close(same_in[k], want[k], 0) < (1e-8 if k == 2 else 1e-12), nm
+        assert rel_close(resident[k], want[k], 0) < (1e-8 if k == 2 else 1e-9), nm
     # run to run on the device: the re-binning uses FP64 atomics, so agreement to rounding, not bitwise
     again = np.array(ec.thermo(cosc, ptc, zp, sp.T))
     assert rel_close(again, resident, 0) < 1e-13
