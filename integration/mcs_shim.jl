@@ -25,7 +25,8 @@
 module McsShim
 
 export McsConfig, McsSpecies, McsPopulation, McsInjection, McsTallies, McsTraceRec, McsTiming
-export create, destroy, check_abi, default_config, set_profile!, begin_ion!, run_ion!, end_ion!, run_ion_gpu!, f64ptr
+export create, destroy, check_abi, default_config, set_profile!, begin_ion!, run_ion!, end_ion!, run_ion_gpu!, thermo_gpu, f64ptr
+export McsThermoIn
 
 const LIBMCS = get(ENV, "MCS_LIB", joinpath(@__DIR__, "..", "montecarloscattering.jl_b200", "libmcs_b200.so"))
 
@@ -208,6 +209,16 @@ struct McsTiming
     local_reds::Int64
 end
 
+struct McsThermoIn
+    cos_center::Ptr{Float64}
+    pt_center::Ptr{Float64}
+    zone_pop::Ptr{Float64}
+    temperature_K::Float64
+    psd::Ptr{Float64}
+    therm_d2N_pf::Ptr{Float64}
+    num_crossings::Ptr{Int64}
+end
+
 # ---- plumbing ---------------------------------------------------------------------------------------------------------
 
 last_error() = unsafe_string(ccall((:mcs_last_error, LIBMCS), Cstring, ()))
@@ -337,6 +348,25 @@ function end_ion!(h, s::TallyScratch)
         0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0, 0, 0, 0, ntuple(_ -> Int64(0), 6)))
     GC.@preserve s check(ccall((:mcs_end_ion, LIBMCS), Cint, (Ptr{Cvoid}, Ref{McsTallies}), h, t))
     return t[]
+end
+
+"""
+    thermo_gpu(h, n_grid, cos_center, pt_center, zone_pop, T₀) -> (P_psd_par, P_psd_perp, energy_density_psd)
+
+Drop-in for the `thermo_calcs(...)` call of ion_finalize.jl:38-47, after `end_ion!` of the same ion (needs
+`bin_thermal = 1` in the McsConfig: the thermal crossings are then binned as they happen and the crossing log /
+scratch file of thermo_calcs.jl:96-164 is not read).  `cos_center` (0:num_psd_θ_bins) and `pt_center`
+(0:num_psd_mom_bins, in g cm/s) are the two arrays thermo_calcs.jl:55-82 builds, `zone_pop` is the one
+get_normalized_dNdp returns (ion_finalize.jl:25); pass their parents / ustrip'ed payloads.  Results are plain
+Float64 in cgs (dyn/cm², erg/cm³).
+"""
+function thermo_gpu(h, n_grid, cos_center::Vector{Float64}, pt_center::Vector{Float64}, zone_pop::Vector{Float64}, T₀::Float64)
+    P_par, P_perp, e_dens = zeros(n_grid), zeros(n_grid), zeros(n_grid)
+    tin = Ref(McsThermoIn(pointer(cos_center), pointer(pt_center), pointer(zone_pop), T₀, C_NULL, C_NULL, C_NULL))
+    GC.@preserve cos_center pt_center zone_pop P_par P_perp e_dens check(ccall((:mcs_thermo, LIBMCS), Cint,
+        (Ptr{Cvoid}, Ref{McsThermoIn}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        h, tin, P_par, P_perp, e_dens, C_NULL))
+    return P_par, P_perp, e_dens
 end
 
 """

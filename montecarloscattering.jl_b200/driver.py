@@ -121,7 +121,7 @@ def run_ion_host_comm(engine: abi.Engine, pcuts, p_pcut_hi, n_pts_pcut, n_pts_pc
 
 _REDUCE_F = ("pxx_flux", "pxz_flux", "energy_flux", "psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream",
              "esc_energy_eff", "esc_num_eff", "weight_coupled", "spectra_coupled", "energy_transfer_pool",
-             "spectra_sf", "spectra_pf")
+             "spectra_sf", "spectra_pf", "therm_d2N_sf", "therm_d2N_pf", "dNdp_cr_sf")
 
 
 def reduce_tallies_host(t: abi.Tallies, comm) -> abi.Tallies:
@@ -146,7 +146,7 @@ def reduce_tallies_host(t: abi.Tallies, comm) -> abi.Tallies:
 def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = None, comm=None,
                device_comm: bool = False, want_psd: bool = True, want_log: bool = True, profile_update=None,
                host_pcut_loop: bool = False, shuffle_population: bool = False, generate_in_library: bool = False,
-               only_ions=None, pop_seed_offset: int = 0):
+               only_ions=None, pop_seed_offset: int = 0, thermo: bool = False):
     """loop_itr / loop_ion / loop_pcut of main_loops.jl:52-341.
 
     Returns a list (per iteration) of lists (per ion) of dicts with the per-ion tallies (pure sums),
@@ -154,6 +154,8 @@ def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = No
     bookkeeping.  `comm` shards the population over ranks; `device_comm` means the engine already
     reduces inside the library (NCCL) so the host must not reduce again.  `generate_in_library` hands init_pop to the
     library in run-length form (mcs_begin_ion_generate): nothing per-particle is drawn or copied by the host.
+    `thermo` (engine built with bin_thermal) adds what ion_finalize.jl:38-47 gets from thermo_calcs — P_psd_par, P_psd_perp,
+    energy_density_psd, d2N_pop per zone — computed by mcs_thermo on the tallies where they lie.
     """
     inp = run.inp
     prof = run.profile
@@ -193,7 +195,14 @@ def main_loops(run: problem.Run, engine: abi.Engine, *, n_iters: int | None = No
             if comm is not None and not device_comm:
                 reduce_tallies_host(t, comm)
             pool = pool + t.energy_transfer_pool
-            per_ion.append(dict(
+            th = {}
+            if thermo:
+                cosc, ptc, zone_pop = problem.thermo_inputs(run, prof, i_ion - 1)
+                host = comm is not None and not device_comm      # the sums over ranks exist on the host only
+                res = engine.thermo(cosc, ptc, zone_pop, sp.T, **(dict(psd=t.psd, therm_d2N_pf=t.therm_d2N_pf,
+                                                                        num_crossings=t.num_crossings) if host else {}))
+                th = dict(zip(("P_psd_par", "P_psd_perp", "energy_density_psd", "d2N_pop"), res), zone_pop=zone_pop)
+            per_ion.append(dict(**th,
                 tallies=t, n_pcuts_run=n_run, n_used=n_used, n_saved=n_saved, n_pts_inj=n,
                 pxx_flux=ip.pxx_flux + t.pxx_flux + 1.0e-99, pxz_flux=ip.pxz_flux + t.pxz_flux + 1.0e-99,
                 energy_flux=ip.energy_flux + t.energy_flux + 1.0e-99, weight_running=ip.weight_running,

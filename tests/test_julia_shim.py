@@ -54,7 +54,7 @@ def c_layout(fields):
     return res, (off + maxal - 1) // maxal * maxal
 
 
-@pytest.mark.parametrize("name", ["McsConfig", "McsSpecies", "McsTallies", "McsPopulation", "McsInjection", "McsTraceRec", "McsTiming"])
+@pytest.mark.parametrize("name", ["McsConfig", "McsSpecies", "McsTallies", "McsPopulation", "McsInjection", "McsTraceRec", "McsTiming", "McsThermoIn"])
 def test_struct_layout_matches_ctypes(name):
     structs = parse_structs(open(SHIM).read())
     assert name in structs, f"{name} missing from mcs_shim.jl"

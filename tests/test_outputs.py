@@ -63,3 +63,27 @@ def test_mc_grid_golden(olib):
     want = outputs.read_mc_grid(path)
     ok = np.isfinite(want)
     assert np.allclose(pick[ok], want[ok], rtol=1e-8, atol=0)
+
+
+def test_thermo_pressures_feed_the_grid_table(olib):
+    """f1 -> f4: main_loops(thermo=True) returns what ion_finalize.jl:38-47 gets from thermo_calcs; handed to the grid table
+    the PSD pressure columns (smoothers.jl:186-203) hold log10 of them and the anisotropy 2 P_par / P_perp."""
+    inp = problem.planar_test_particle_input(1500, momentum_cutoffs=LADDER[:4], fixed_grid=True)
+    run = problem.setup_run(inp)
+    res = driver.main_loops(run, make_engine(olib, run, bin_thermal=True), n_iters=1, want_log=False, thermo=True)[0][0]
+    par, perp = res["P_psd_par"], res["P_psd_perp"]
+    assert par.shape == (run.n_grid,) and np.all(np.isfinite(par)) and np.all(par > 0) and np.all(perp > 0)
+    rows = outputs.mc_grid_table(run, run.profile, res["pxx_flux"], res["energy_flux"], P_psd_par=par, P_psd_perp=perp)
+    col = {n: k for k, n in enumerate(outputs.MC_GRID_COLUMNS)}
+    assert np.allclose(rows[:, col["log_P_psd_par"]], np.log10(par)) and np.allclose(rows[:, col["log_P_tot_MC"]], np.log10(par + perp))
+    assert np.allclose(rows[:, col["P_aniso"]], 2 * par / perp)
+    # far upstream nothing but the cold beam: zones no thermal particle crossed get the analytic isotropic pressure (case 1)
+    t = res["tallies"]
+    quiet = (t.num_crossings == 0) & (t.psd.sum(axis=(1, 2)) == 0)
+    if quiet.any():
+        assert np.allclose(rows[quiet, col["P_aniso"]], 1.0, rtol=1e-12)
+    # downstream of the shock the shocked gas is hot: the PSD pressure exceeds the far-upstream thermal pressure by orders
+    x = rows[:, col["x_rg"]]
+    dn = (x > 0.3) & (x < 5.0) & (t.num_crossings > 0)
+    P0 = sum(s.n0 * s.T for s in run.species) * problem.KB
+    assert dn.sum() > 5 and np.all((par + perp)[dn] > 100 * P0)
