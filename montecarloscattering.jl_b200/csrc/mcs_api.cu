@@ -145,6 +145,7 @@ struct McsHandle {
     bool ended = false;               // mcs_end_ion has folded the accumulators: d_tally holds this ion's final FP64 tallies
     bool split_timed = false;         // ev2/ev3 bracket an un-timed split (elapsed time read at the next sync)
     unsigned long long steps0 = 0, saved0 = 0, reds0 = 0;  // counter values before the pcut in flight
+    double last_steps_per_particle = 0;  // of the previous pcut of this ion (0: none yet); picks the kernel build
     McsTiming tm;
     DevParams P;
 };
@@ -413,7 +414,7 @@ extern "C" int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const 
         if (pop->grid[i] < 0 || pop->grid[i] > h->ng + 1) return fail(MCS_ERR_ARG, "grid index out of range");
     { int rcg = check_index_range(first_global, n); if (rcg) return rcg; }
     CU(cudaSetDevice(h->device));
-    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->ended = false; h->split_timed = false;
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->ended = false; h->split_timed = false; h->last_steps_per_particle = 0;
     h->n_use = n; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     // clear_psd! (ion_init.jl:1-16) and every other per-ion sum
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
@@ -459,7 +460,7 @@ extern "C" int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_io
     { int rcg = check_index_range(first_global, n_local); if (rcg) return rcg; }
     if (n_total > 0x100000000ll) return fail(MCS_ERR_ARG, "global particle index exceeds 2^32 (RNG counter width)");
     CU(cudaSetDevice(h->device));
-    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->ended = false; h->split_timed = false;
+    h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->reduced = false; h->ended = false; h->split_timed = false; h->last_steps_per_particle = 0;
     h->n_use = n_local; h->first_global = first_global; h->n_saved_last = 0; h->n_saved_global_last = 0;
     CU(cudaMemsetAsync(h->d_tally, 0, h->n_tally * 8, h->stream));
     if (h->d_acc) CU(cudaMemsetAsync(h->d_acc, 0, h->n_tally * ACC_D * 8, h->stream));
@@ -550,10 +551,17 @@ static int launch_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_pr
         const size_t smem = block_smem_bytes(h->ng, h->block / 32);
         const bool electron = h->sp.aa < 1;
         const bool obl = P.oblique != 0;  // only the fast loop reads it: the debug build has none
+        // SLIM build of the fast loop (drain helpers out of line) for short trajectories, where the warps go back and forth
+        // between the loop and the general section and wait for instruction fetch; the arithmetic is the same.  Chosen from
+        // the previous pcut of this ion: fewer than 2000 scattering steps per particle (MCS_SLIM_DRAIN=0/1 forces it).
+        const int slim_env = env_int("MCS_SLIM_DRAIN", -1);
+        const bool slim = slim_env >= 0 ? slim_env != 0 : (h->last_steps_per_particle > 0 && h->last_steps_per_particle < 2000.0);
         void (*kern)(const DevParams) =
-            debug ? (electron ? transport_kernel<true, true, false> : transport_kernel<true, false, false>)
-                  : (electron ? (obl ? transport_kernel<false, true, true> : transport_kernel<false, true, false>)
-                              : (obl ? transport_kernel<false, false, true> : transport_kernel<false, false, false>));
+            debug ? (electron ? transport_kernel<true, true, false, false> : transport_kernel<true, false, false, false>)
+            : slim ? (electron ? (obl ? transport_kernel<false, true, true, true> : transport_kernel<false, true, false, true>)
+                               : (obl ? transport_kernel<false, false, true, true> : transport_kernel<false, false, false, true>))
+                   : (electron ? (obl ? transport_kernel<false, true, true, false> : transport_kernel<false, true, false, false>)
+                               : (obl ? transport_kernel<false, false, true, false> : transport_kernel<false, false, false, false>));
         // per function and per device, not per handle: set for THIS launch (another handle may have a smaller grid)
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -585,6 +593,7 @@ static int finish_pcut(McsHandle* h, int64_t* n_saved, int64_t* n_steps) {
     h->n_saved_last = (long long)(h->h_counters[CNT_FATE0] - h->saved0);
     h->tm.local_steps += st;
     h->tm.local_particles += h->n_use;
+    h->last_steps_per_particle = h->n_use > 0 ? (double)st / (double)h->n_use : 0.0;
     h->tm.local_reds += (int64_t)(h->h_counters[CNT_RED] - h->reds0);
     if (n_saved) *n_saved = h->n_saved_last;
     if (n_steps) *n_steps = st;

@@ -235,9 +235,15 @@ __device__ __forceinline__ void count(const DevParams& P, int which, unsigned lo
 constexpr int ACC_D = 10;
 constexpr int ACC_ELO = -210;
 __device__ __forceinline__ int acc_add(const DevParams& P, size_t cell, double v);
+__device__ __noinline__ int acc_add_ool(const DevParams& P, size_t cell, double v);
 // one tally update: exact accumulator when configured, else an FP64 red into the cell itself
+// OOL: call the one out-of-line copy of the accumulator add / bin evaluation.  Everything outside the fast loop does (the
+// general section, the shared copy of the drain): inlined, each copy of the drain was 5000 instructions (80 KB), and the
+// instruction caches are what the many-short-pcut ladders wait for (no_instruction 32 % of the stall samples at gamma0 = 10).
+// The drain folded into the fast loop keeps them inline (calls there cost the planar config ~1 %).
+template <bool OOL = true>
 __device__ __forceinline__ int tally_add(const DevParams& P, double* cell, double v) {
-    if (P.t.acc != nullptr) return acc_add(P, (size_t)(cell - P.t.tally_base), v);
+    if (P.t.acc != nullptr) return OOL ? acc_add_ool(P, (size_t)(cell - P.t.tally_base), v) : acc_add(P, (size_t)(cell - P.t.tally_base), v);
     red_add_f64(cell, v);
     return 1;
 }
@@ -267,6 +273,7 @@ __device__ __forceinline__ int acc_add(const DevParams& P, size_t cell, double v
     if (d2) { red_add_u64(c + 2, d2); n++; }
     return n;
 }
+__device__ __noinline__ int acc_add_ool(const DevParams& P, size_t cell, double v) { return acc_add(P, cell, v); }
 
 // RNG: Philox4x32-10, counter = (block, i_prt, i_pcut | i_ion<<16, i_iter), key = seed. Replaces the
 // per-particle Random.Xoshiro(iseed_mod) of particle_loop.jl:34-41.  Integer pipe only.
@@ -397,6 +404,16 @@ __device__ __forceinline__ int psd_bin_angle(const DevParams& P, double px_sk, d
         bin = th < P.psd_theta_min ? 0 : (int)trunc(log10(th / P.psd_theta_min) * P.bpd_th) + 1;
     }
     return min(bin, P.T);
+}
+__device__ __noinline__ int psd_bin_momentum_ool(const DevParams& P, double ptot_sk, int uses) { return psd_bin_momentum(P, ptot_sk, uses); }
+__device__ __noinline__ int psd_bin_angle_ool(const DevParams& P, double px_sk, double ptot_sk) { return psd_bin_angle(P, px_sk, ptot_sk); }
+template <bool OOL>
+__device__ __forceinline__ int bin_mom(const DevParams& P, double ptot_sk, int uses = 1) {
+    return OOL ? psd_bin_momentum_ool(P, ptot_sk, uses) : psd_bin_momentum(P, ptot_sk, uses);
+}
+template <bool OOL>
+__device__ __forceinline__ int bin_ang(const DevParams& P, double px_sk, double ptot_sk) {
+    return OOL ? psd_bin_angle_ool(P, px_sk, ptot_sk) : psd_bin_angle(P, px_sk, ptot_sk);
 }
 
 // transformers.jl:440-476 (uz, utot do not enter the parallel-to-x boost as written)
@@ -545,7 +562,7 @@ __device__ __forceinline__ double radiation_loss(const DevParams& P, double B2, 
 // cuts.jl:149-162
 __device__ __noinline__ void tcut_track(const DevParams& P, int tcut_curr, double weight, double ptot) {
     int n = tally_add(P, &P.t.w_coupled[tcut_curr - 1], weight);
-    int ip = psd_bin_momentum(P, ptot);
+    int ip = psd_bin_momentum_ool(P, ptot, 1);
     n += tally_add(P, &P.t.s_coupled[ip + E1 * (tcut_curr - 1)], weight);
     count(P, CNT_RED, (unsigned long long)n);
 }
@@ -659,7 +676,7 @@ __device__ __noinline__ int bin_thermal_crossing(const DevParams& P, int lo, int
     int n_at = 0;
     const double w = weight * (ptot_sk > fabs(sx * SPIKE_AWAY) ? fabs(SPIKE_AWAY / ux) : fabs(gam_sk * P.aa * P.mp / sx));
     const size_t sT = (size_t)(P.T + 2), sM = (size_t)(P.M + 2);
-    const int k = psd_bin_momentum(P, ptot_sk), jt = psd_bin_angle(P, sx, ptot_sk);
+    const int k = psd_bin_momentum_ool(P, ptot_sk, 1), jt = psd_bin_angle_ool(P, sx, ptot_sk);
     const double E0 = P.m * (P.c * P.c), etot = hypot(ptot_sk * P.c, E0);
     for (int i = lo; i <= hi; i++) {
         n_at += tally_add(P, &P.t.therm_sf[(size_t)jt + sT * ((size_t)k + sM * (size_t)(i - 1))], w);
@@ -667,7 +684,7 @@ __device__ __noinline__ int bin_thermal_crossing(const DevParams& P, int lo, int
         double pxX = g * (sx - b * etot / P.c);
         const double ptX = sqrt((ptot_sk * ptot_sk - sx * sx) + pxX * pxX);
         if (fabs(pxX) > ptX) pxX = copysign(ptX, pxX);
-        const int kX = psd_bin_momentum(P, ptX), jX = psd_bin_angle(P, pxX, ptX);
+        const int kX = psd_bin_momentum_ool(P, ptX, 1), jX = psd_bin_angle_ool(P, pxX, ptX);
         n_at += tally_add(P, &P.t.therm_pf[(size_t)jX + sT * ((size_t)kX + sM * (size_t)(i - 1))], w);
     }
     return n_at;
@@ -679,6 +696,21 @@ __device__ __noinline__ int bin_thermal_crossing(const DevParams& P, int lo, int
 //                     upstream-FEB scalars);
 //   finish event   -> particle_finish.jl:46-107 and the downstream sums of particle_loop.jl:478-495.
 // The n_grid-sized tallies and the scalars go to this warp's shared partials with plain adds in event order.
+// Converged: butterfly sums (fixed order) of the escape / downstream scalars of one batch of events into the warp's partials.
+__device__ __noinline__ void reduce_scalars(double s0, double s1, double s2, double s3, double s4, double s5, double s6, int ng) {
+    static_assert(SC_N - 1 == 7, "reduce_scalars takes the first SC_N - 1 scalars");
+    const WarpMem wm = warp_mem(threadIdx.x >> 5, ng);
+    const int lane = threadIdx.x & 31;
+    double v[7] = {s0, s1, s2, s3, s4, s5, s6};
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        double t = v[k];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+        if (lane == 0) wm.part[3 * ng + k] += t;
+    }
+}
+
+template <bool OOL>
 __device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) {
     const int lane = threadIdx.x & 31, ng = P.n_grid;
     const WarpMem wm = warp_mem(threadIdx.x >> 5, ng);
@@ -719,12 +751,12 @@ __device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) 
         const uint32_t xmask = fl >> EV_XSPEC_SHIFT;
         if (xmask) {  // calculate_x_spec_spectra! :164-190
             double pt_o_px_pf = fmin(fabs(ptot / pb), SPIKE_AWAY);
-            int ipt = psd_bin_momentum(P, ptot_sk), ipf = psd_bin_momentum(P, ptot);
+            int ipt = bin_mom<OOL>(P, ptot_sk), ipf = bin_mom<OOL>(P, ptot);
             for (int i = 0; i < P.n_xspec; i++)
                 if (xmask & (1u << i)) {
-                    n_red += tally_add(P, &P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
+                    n_red += tally_add<OOL>(P, &P.t.spec_sf[ipt + E1 * i], weight * pt_o_px_sk);
                     double F = fabs(pb / sx) * (gam_sk / gam_pf);
-                    n_red += tally_add(P, &P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
+                    n_red += tally_add<OOL>(P, &P.t.spec_pf[ipf + E1 * i], weight * pt_o_px_pf * F);
                 }
         }
         const double sign_fac = up ? -1.0 : 1.0;
@@ -736,10 +768,10 @@ __device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) 
         if (lo <= hi) {
             const double w = weight * abs_inv_vx;
             if (inj) {
-                int ipt = psd_bin_momentum(P, ptot_sk), jth = psd_bin_angle(P, sx, ptot_sk);
+                int ipt = bin_mom<OOL>(P, ptot_sk), jth = bin_ang<OOL>(P, sx, ptot_sk);
                 const size_t stride = (size_t)(P.M + 2) * (size_t)(P.T + 2);
                 double* cell = P.t.psd + (size_t)ipt + (size_t)(P.M + 2) * (size_t)jth + stride * (size_t)(lo - 1);
-                for (int i = lo; i <= hi; i++, cell += stride) n_red += tally_add(P, cell, w);
+                for (int i = lo; i <= hi; i++, cell += stride) n_red += tally_add<OOL>(P, cell, w);
             } else {
                 thermal = true;
                 n_red += hi - lo + 1;  // crossing counts
@@ -781,22 +813,22 @@ __device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) 
         const int reason = (fl >> EV_REASON_SHIFT) & 7;
         const double E0 = P.m * (P.c * P.c);
         if (reason == 1 || reason == 2) {
-            int ip = min(psd_bin_momentum(P, ptot_sk), MCS_PSD_MAX), jt = min(psd_bin_angle(P, sx, ptot_sk), MCS_PSD_MAX);
+            int ip = min(bin_mom<OOL>(P, ptot_sk), MCS_PSD_MAX), jt = min(bin_ang<OOL>(P, sx, ptot_sk), MCS_PSD_MAX);
             double wf;
             if (ptot_sk > fabs(SPIKE_AWAY * sx)) wf = gam_sk * P.m * SPIKE_AWAY / ptot_sk;
             else wf = gam_sk * (P.m / fabs(sx));
             if (reason == 1) {
-                n_red += tally_add(P, &P.t.esc_dn[ip + E1 * jt], weight * wf);
+                n_red += tally_add<OOL>(P, &P.t.esc_dn[ip + E1 * jt], weight * wf);
             } else {
                 sc[SC_ESC_FLUX] = weight;
-                n_red += tally_add(P, &P.t.esc_up[ip + E1 * jt], weight * wf);
+                n_red += tally_add<OOL>(P, &P.t.esc_up[ip + E1 * jt], weight * wf);
                 bool rel = (gam_sk - 1) >= P.E_rel_pt;  // F-8
                 double Ek = rel ? (gam_sk - 1) * E0 : ptot_sk * ptot_sk / (2 * P.m);
                 double en_add = Ek * weight;
                 sc[SC_PX_ESC_FEB] = fabs(sx) * weight;
                 sc[SC_EN_ESC_FEB] = en_add;
-                n_red += tally_add(P, &P.t.esc_en_eff[ip], en_add);
-                n_red += tally_add(P, &P.t.esc_num_eff[ip], weight);
+                n_red += tally_add<OOL>(P, &P.t.esc_en_eff[ip], en_add);
+                n_red += tally_add<OOL>(P, &P.t.esc_num_eff[ip], weight);
             }
         }
         if (fl & EV_SUMP) {  // particle_loop.jl:478-486
@@ -845,12 +877,7 @@ __device__ MCS_COLD void process_events(const DevParams& P, int base, int n_ev) 
 #pragma unroll
     for (int k = 0; k < SC_N; k++) any_sc |= sc[k] != 0.0;
     if (__any_sync(FULL, any_sc)) {
-#pragma unroll
-        for (int k = 0; k < SC_N - 1; k++) {
-            double v = sc[k];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);  // fixed butterfly order
-            if (lane == 0) wm.part[3 * ng + k] += v;
-        }
+        reduce_scalars(sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], ng);  // rare (finish / FEB events): one shared copy
     }
     for (int o = 16; o > 0; o >>= 1) n_red += __shfl_xor_sync(FULL, n_red, o);
     if (lane == 0 && n_red > 0) count(P, CNT_RED, (unsigned long long)n_red);
@@ -975,7 +1002,15 @@ struct Lane {
     uint32_t cs_flags;  // ST_RAN | ST_MUSN | ST_PHI carried along
 };
 
+// One shared out-of-line copy of the drain for everything outside the fast loop (the general section's two push sites and
+// the end of the kernel): three fewer inlined copies of ~16 KB each for the instruction caches to hold.
+__device__ __noinline__ void process_events_ool(const DevParams& P, int base, int n_ev) { process_events<true>(P, base, n_ev); }
+
 // Converged: append the lanes' events (ev != 0) to the warp's queue, drain a full batch.  Returns the new queue length.
+// INLINE_DRAIN: the fast loop folds the drain in (an ABI call there forces the loop's registers through local memory).
+// OOL_HELPERS: that folded-in drain calls the out-of-line bin evaluation / accumulator add (the SLIM kernel: 5181 instead of
+// 6743 instructions; +5 % on ladders of many short pcuts, -0.5 % on long ones — chosen per launch by the host, see launch_pcut).
+template <bool INLINE_DRAIN, bool OOL_HELPERS = true>
 __device__ __forceinline__ int push_events(const DevParams& P, const WarpMem& wm, int qn, uint32_t ev, int ip, double pb,
                                            double pperp, double gam_pf, double cphi, double sphi, double ptot, int i_new,
                                            int i_old, int iz) {
@@ -984,7 +1019,7 @@ __device__ __forceinline__ int push_events(const DevParams& P, const WarpMem& wm
         const int cnt = __popc(m);
         if (QCAP < 64 && qn + cnt > QCAP) {  // would not fit: drain what is queued as a partial batch first
             __syncwarp();
-            process_events(P, 0, qn);
+            if (INLINE_DRAIN) process_events<OOL_HELPERS>(P, 0, qn); else process_events_ool(P, 0, qn);
             qn = 0;
         }
         if (ev) {
@@ -996,7 +1031,7 @@ __device__ __forceinline__ int push_events(const DevParams& P, const WarpMem& wm
         qn += cnt;
         if (qn >= 32) {  // sums commute; the order is fixed by the lock-step schedule
             __syncwarp();
-            process_events(P, qn - 32, 32);
+            if (INLINE_DRAIN) process_events<OOL_HELPERS>(P, qn - 32, 32); else process_events_ool(P, qn - 32, 32);
             qn -= 32;
         }
     }
@@ -1277,7 +1312,7 @@ __device__ __noinline__ bool general_section(const DevParams& P, Lane& Lref, con
         {
             double ec = 1.0, es = 0.0;
             if (ev) sincos_bf(phi, &es, &ec);
-            qn = push_events(P, wm, qn, ev, ip, pb, pperp, gam_pf, ec, es, ptot, i_grid, i_grid_old, iz);
+            qn = push_events<false>(P, wm, qn, ev, ip, pb, pperp, gam_pf, ec, es, ptot, i_grid, i_grid_old, iz);
         }
         // ---- rest of Code Block 2: downstream escape / return ------------------------------------------------
         bool sum_p = false;
@@ -1343,7 +1378,7 @@ __device__ __noinline__ bool general_section(const DevParams& P, Lane& Lref, con
         {
             double ec = 1.0, es = 0.0;
             if (ev) sincos_bf(phi, &es, &ec);
-            qn = push_events(P, wm, qn, ev, ip, pb, pperp, gam_pf, ec, es, ptot, i_grid, i_grid_old, iz);
+            qn = push_events<false>(P, wm, qn, ev, ip, pb, pperp, gam_pf, ec, es, ptot, i_grid, i_grid_old, iz);
         }
         if (release) ip = -1;
         // a particle back from retro_time (i_return == 1) takes its follow-up pass here at once
@@ -1405,7 +1440,7 @@ __device__ __forceinline__ double mod2pi_bf(double v, bool& ok) {
 #else
 #define MCS_KERNEL_BOUNDS __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS)
 #endif
-template <bool DEBUG, bool ELECTRON, bool OBLIQUE>
+template <bool DEBUG, bool ELECTRON, bool OBLIQUE, bool SLIM>
 __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char mcs_smem[];
     const int ng = P.n_grid;
@@ -1653,7 +1688,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                 }
                 // converged: queue the crossing events of this pass (state right after the move, as at point A)
                 if (__any_sync(FULL, fev != 0u))
-                    qn = push_events(P, wm, qn, fev, ip, L.ptot * mu, L.ptot * sn, L.gam_pf, cph, sph, L.ptot, (int)(gpack & 0xffffu), ev_old,
+                    qn = push_events<true, SLIM>(P, wm, qn, fev, ip, L.ptot * mu, L.ptot * sn, L.gam_pf, cph, sph, L.ptot, (int)(gpack & 0xffffu), ev_old,
                                      ev_old);
                 // leave the loop?  Enough lanes wait for the general pass, or few have waited long (short trajectories: many
                 // refills), or the bound on consecutive iterations is reached
@@ -1743,7 +1778,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
         }
     }
     __syncwarp();
-    if (L.qn > 0) process_events(P, 0, L.qn);
+    if (L.qn > 0) process_events_ool(P, 0, L.qn);
 
     MCS_SC(count(P, CNT_FAST_LANE, c_fast_lane);
            if (lane == 0) { count(P, CNT_FAST_ITER, c_fast_iter); count(P, CNT_SLOW_SEC, c_sections);

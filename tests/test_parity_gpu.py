@@ -398,6 +398,30 @@ def test_deterministic_tallies_run_to_run(clib):
     assert a.psd.sum() > 0 and a.weight_coupled.sum() > 0
 
 
+def test_both_builds_of_the_fast_loop_agree_bitwise(clib, monkeypatch):
+    """The library carries two builds of the fast loop (drain helpers inline / out of line) and picks one per launch from the
+    previous pcut's steps per particle (mcs_api.cu launch_pcut).  Same arithmetic, same lane schedule: every tally and every
+    saved record must be identical bit for bit whichever build runs — otherwise results would depend on the pick."""
+    run = problem.setup_run(problem.relativistic_input(4000, momentum_cutoffs=problem.DEFAULT_PCUTS[:10]))
+    out = []
+    for force in ("0", "1", None):
+        if force is None:
+            monkeypatch.delenv("MCS_SLIM_DRAIN", raising=False)
+        else:
+            monkeypatch.setenv("MCS_SLIM_DRAIN", force)
+        e = make_engine(clib, run)
+        res = driver.main_loops(run, e, n_iters=1, want_log=False)[0][0]
+        out.append((res["tallies"], res["n_saved"], e.get_population(0)))
+    (a, na, pa), (b, nb, pb), (c, nc, pc) = out
+    assert list(na) == list(nb) == list(nc) and a.stats == b.stats == c.stats and a.stats["n_helix_steps"] > 1e6
+    for nm in ("pxx_flux", "pxz_flux", "energy_flux", "num_crossings", "psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream",
+               "esc_energy_eff", "esc_num_eff", "energy_transfer_pool"):
+        assert np.array_equal(getattr(a, nm), getattr(b, nm)) and np.array_equal(getattr(a, nm), getattr(c, nm)), nm
+    assert a.scalars == b.scalars == c.scalars
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]) and np.array_equal(pa[k], pc[k]), k
+
+
 def test_exact_accumulators_are_schedule_independent_and_match_fp64_sums(clib):
     """The exact accumulators against (i) a different particle-to-lane schedule (dynamic queue): bitwise equal histogram,
     and (ii) the plain FP64 red path (det_tallies = 0): equal to summation order."""
