@@ -218,7 +218,7 @@ def main():
                     help="bench: the workload's own ladder; default: the 45 cut-offs of the reference's mc_in.toml:84-130")
     ap.add_argument("--all-species", action="store_true",
                     help="multi workload: one step = all ion species of the iteration (p, He, e-) with the pool hand-over")
-    ap.add_argument("--cpu-sample", type=int, default=10000, help="particles per pcut of the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=30000, help="particles per pcut of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stat-parity", type=int, default=0, metavar="R",
                     help="cpu_baseline leg: run the CPU sample as R independent replicas (cpu-sample / R particles per pcut each) and "
