@@ -295,8 +295,8 @@ def _multi_gpu_case(clib, n_ranks):
     rebalancing split, one count exchange per pcut — against the same global population on one rank."""
     import threading
     run = problem.setup_run(problem.planar_test_particle_input(4000, momentum_cutoffs=LADDER[:4]))
-    one = driver.main_loops(run, make_engine(clib, run), n_iters=1)[0][0]
-    engs = [make_engine(clib, run, device=d) for d in range(n_ranks)]
+    one = driver.main_loops(run, make_engine(clib, run, bin_thermal=True), n_iters=1, thermo=True)[0][0]
+    engs = [make_engine(clib, run, device=d, bin_thermal=True) for d in range(n_ranks)]
     uid = engs[0].comm_unique_id()
     out, err = [None] * n_ranks, [None] * n_ranks
 
@@ -307,7 +307,7 @@ def _multi_gpu_case(clib, n_ranks):
     def work(r):
         try:
             engs[r].comm_init(r, n_ranks, uid)
-            out[r] = driver.main_loops(run, engs[r], n_iters=1, comm=Ranks(r), device_comm=True)[0][0]
+            out[r] = driver.main_loops(run, engs[r], n_iters=1, comm=Ranks(r), device_comm=True, thermo=True)[0][0]
         except Exception as e:  # noqa: BLE001 - reported below, in the main thread
             err[r] = e
 
@@ -322,8 +322,12 @@ def _multi_gpu_case(clib, n_ranks):
         assert np.array_equal(ta.num_crossings, tb.num_crossings)
         assert rel_close(out[r]["pxx_flux"], one["pxx_flux"], 0) < 1e-11
         # exact accumulators: the histograms do not depend on how the particles were spread over GPUs
-        for nm in ("psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream", "esc_energy_eff", "esc_num_eff"):
+        for nm in ("psd", "esc_psd_feb_upstream", "esc_psd_feb_downstream", "esc_energy_eff", "esc_num_eff", "therm_d2N_sf",
+                   "therm_d2N_pf"):
             assert np.array_equal(getattr(ta, nm), getattr(tb, nm)), nm
+        # the pressure consumer reads the all-reduced tallies resident on each rank: every rank gets the one-GPU answer
+        for nm in ("P_psd_par", "P_psd_perp", "energy_density_psd", "d2N_pop"):
+            assert rel_close(out[r][nm], one[nm], 0) < 1e-12, nm
 
 
 def test_two_gpu_nccl_matches_one_gpu(clib):
