@@ -1465,8 +1465,8 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
 
     const uint32_t flags = P.flags;
     // the fast loop covers scattering configurations without per-pass field updates, detectors or debug streams
-    const bool fast_ok = !DEBUG && !(flags & (F_CUSTOM_EPSB | F_DONT_SCATTER | F_NO_FAST_LOOP)) &&
-                         !(ELECTRON && (flags & F_RAD_LOSSES)) && P.n_xspec == 0;
+    const bool fast_ok = !DEBUG && !(flags & (F_CUSTOM_EPSB | F_DONT_SCATTER | F_NO_FAST_LOOP)) && P.n_xspec == 0;
+    const bool rad_fast = ELECTRON && (flags & F_RAD_LOSSES);  // the fast loop applies radiation_loss itself, pass by pass
     const bool reflect_cfg = (flags & F_DONT_DSA) || P.inj_frac < 1;
 
     Lane L;
@@ -1559,9 +1559,27 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         // sine and cosine come from the table; sqrt(w) is w * rsqrt(w) and the three of them overlap
                         // (sin_new and the pair (sv, cv) = (sin, cos) of the phase change asin(sv) share one reciprocal
                         // square root of sn2); the phase change is applied as a rotation.
-                        const bool xs_n = x > grt;                                   // particle_loop.jl:385, decided first
+                        // Electrons with radiative losses (particle_loop.jl:578-592, applied where the general pass applies it:
+                        // over the PREVIOUS pass's time step, after the zone change, before the kick).  The momentum and what
+                        // hangs on it — Lorentz factor, gyro-radius, gyro-period, speed — become per-pass quantities; mu and sn
+                        // do not change (pb and pperp shrink by the same factor).  Held in temporaries until the pass commits.
+                        double p_use = 0.0, gam_use = 0.0, grt_u = grt, vgm_u = vgm, gper_u = gper;
+                        bool lost_all = false;
+                        if (ELECTRON && rad_fast) {
+                            const double bmag = P.bt[iz], Bcmb = P.B_CMBz * zt.b[iz].x;
+                            p_use = radiation_loss(P, bmag * bmag + Bcmb * Bcmb, L.ptot, t_step);
+                            lost_all = !(p_use > 0.0);                               // fate 4: the general pass ends it
+                            gam_use = hypot(p_use / P.mc, 1.0);
+                            const double gd_z = zt.gd[iz];
+                            grt_u = p_use * P.c * gd_z;
+                            vgm_u = p_use * (1 / (gam_use * P.m));
+                            gper_u = p_use < P.pe_crit ? TWO_PI * P.gam_e_crit * P.mc * gd_z : TWO_PI * gam_use * P.mc * gd_z;
+                        } else if (ELECTRON) {
+                            p_use = L.ptot; gam_use = L.gam_pf;
+                        }
+                        const bool xs_n = x > grt_u;                                 // particle_loop.jl:385, decided first
                         const int xi = xs_n ? 1 : 0;
-                        const double t_n = gper * P.inv_xn[xi];
+                        const double t_n = gper_u * P.inv_xn[xi];
                         const double cd = P.cdphi[xi], sd = P.sdphi[xi];
                         const double omc = P.omc[(st & ST_XSEL) ? 1 : 0];
                         const uint32_t odd = rng_n & 1u;
@@ -1594,7 +1612,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         // Code Block 2 move
                         const double cph_n = c1 * cd - s1 * sd, sph_n = s1 * cd + c1 * sd;
                         const double2 za = zt.a[iz], zb = zt.b[iz], zc = zt.c[iz];  // {ux, gsf} {gef, cos th} {xg[iz], xg[iz+1]}
-                        const double x_move = (cos_new * vgm) * t_n;
+                        const double x_move = (cos_new * vgm_u) * t_n;
                         double gyr = 0.0;
                         if (OBLIQUE) {
                             const double bsin = P.sinth[iz];
@@ -1612,6 +1630,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         // `other`: anything but a zone change inside the grid (also a NaN position: !(NaN < stop))
                         const bool beyond = !(x_n < P.x_grid_stop);
                         bool other = !(sn2 > 0.0) | park | (beyond & ((x < P.x_grid_stop) | !(x_n < prp_x) | ELECTRON));
+                        if (ELECTRON) other |= lost_all;
                         if (st & ST_INJ) other |= x_n < P.feb_up;
                         if (P.feb_dn > 0) other |= x_n > P.feb_dn;
                         if (reflect_cfg) other |= (x_n <= 0) & (x > 0);
@@ -1625,26 +1644,29 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                             bool pk = false;
                             const bool cross_down = x < 0 && x_n >= 0;
                             if (cross_down) {  // particle_loop.jl:413-429: arrival downstream, make the region long enough
-                                const double Ld = P.eta_mfp / 3 * grt * L.ptot / (P.m * L.gam_pf * P.u2);
+                                const double Ld = ELECTRON ? P.eta_mfp / 3 * grt_u * p_use / (P.m * gam_use * P.u2)
+                                                           : P.eta_mfp / 3 * grt * L.ptot / (P.m * L.gam_pf * P.u2);
                                 prp_n = fmax(prp_x, Ld);
                             }
                             if (other) {
                             // anything the general pass would have to act on after the move -> nothing is committed
                             pk = park | !(sn2 > 0.0) | !(x_n == x_n) | (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) |
-                                 (P.feb_dn > 0 && x_n > P.feb_dn);
+                                 (P.feb_dn > 0 && x_n > P.feb_dn) | (ELECTRON && lost_all);
                             // (not `other`: x_n < x_grid_stop <= prp_x, or x_grid_stop <= x, x_n < prp_x — neither test below fires)
                             if (x_n > 1.1 * prp_n) {
                                 // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes beyond 6.91 L_diff
                                 double v_fac;
-                                if (ELECTRON && L.ptot < P.pe_crit) v_fac = (P.pe_crit * P.c * zt.gd[iz]) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
+                                if (ELECTRON && p_use < P.pe_crit) v_fac = (P.pe_crit * P.c * zt.gd[iz]) * P.pe_crit / (P.m * P.gam_e_crit * P.u2);
+                                else if (ELECTRON) v_fac = grt_u * p_use / (P.m * gam_use * P.u2);
                                 else v_fac = grt * L.ptot / (P.m * L.gam_pf * P.u2);
                                 pk |= x_n > 6.91 * (P.eta_mfp / 3 * v_fac);
                             }
                             if (x_n >= P.x_grid_stop) {
                                 if (x < P.x_grid_stop) {
                                     // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP
-                                    const double g2 = L.ptot * P.c * 1.0 / (P.qcgs * P.bmag2);
-                                    prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * L.ptot / (P.aa * P.mp * L.gam_pf * P.u2));
+                                    const double p_g = ELECTRON ? p_use : L.ptot, gam_g = ELECTRON ? gam_use : L.gam_pf;
+                                    const double g2 = p_g * P.c * 1.0 / (P.qcgs * P.bmag2);
+                                    prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * p_g / (P.aa * P.mp * gam_g * P.u2));
                                 } else {
                                     pk |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test
                                 }
@@ -1676,6 +1698,11 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                             prp_x = prp_n;
                             helix++; MCS_SC(c_fast_lane++;)
                             acct = acct_n; t_step = t_n;
+                            if (ELECTRON && rad_fast) {  // the loss of this pass becomes the particle's momentum
+                                grt = grt_u; vgm = vgm_u; gper = gper_u;
+                                L.ptot = p_use; L.gam_pf = gam_use; L.grt = grt_u;
+                                L.inv_ptot = 1 / p_use; L.inv_gm = 1 / (gam_use * P.m);
+                            }
                             mu = cos_new; sn = sin_new; cph = cph_n; sph = sph_n; x = x_n;
                             gpack = (uint32_t)ig_new | ((uint32_t)iz << 16);
                             rng_n += 2; rng_s2 = l2; rng_s3 = l3;
@@ -1755,6 +1782,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         L.phi = a;
                     }
                     if (st & ST_MUSN) { L.pb = L.ptot * mu; L.pperp = L.ptot * sn; }
+                    if (ELECTRON && rad_fast) L.gr = L.pperp * P.c * L.gd;
                     L.cs_valid = false;
                 } else {
                     // the warp left because of other lanes: this one comes back with exactly these registers

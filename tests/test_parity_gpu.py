@@ -346,18 +346,23 @@ def test_all_visible_gpus_nccl_match_one_gpu(clib):
     _multi_gpu_case(clib, n)
 
 
-def test_fast_loop_matches_general_path(clib, monkeypatch):
+@pytest.mark.parametrize("case", ["protons", "electrons_with_losses"])
+def test_fast_loop_matches_general_path(clib, monkeypatch, case):
     """The two-speed kernel (fast loop + lane parking) against the same kernel with every pass on the general path
     (MCS_NO_FAST_LOOP=1): per particle the sequence of operations is the same, so integers are identical and the
-    continuous state agrees to rounding (the two code paths may contract FMAs differently)."""
-    inp = problem.planar_test_particle_input(20_000, momentum_cutoffs=LADDER[:5])
+    continuous state agrees to rounding (the two code paths may contract FMAs differently).  Electrons of config 5:
+    radiation_loss applied pass by pass inside the fast loop (momentum, Lorentz factor, gyro-radius and speed per pass)."""
+    if case == "protons":
+        inp, i_ion = problem.planar_test_particle_input(20_000, momentum_cutoffs=LADDER[:5]), 1
+    else:
+        inp, i_ion = problem.multi_species_input(3000, momentum_cutoffs=problem.DEFAULT_PCUTS[:4]), 3
     run = problem.setup_run(inp)
-    sp = run.species[0]
+    sp = run.species[i_ion - 1]
     res = []
     for no_fast in ("0", "1"):
         monkeypatch.setenv("MCS_NO_FAST_LOOP", no_fast)
         e = make_engine(clib, run)
-        start_ion(e, run)
+        start_ion(e, run, i_ion=i_ion)
         out = []
         for k, pcut in enumerate(run.pcuts, start=1):
             n = e.population_size()
