@@ -556,8 +556,10 @@ static int launch_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_pr
         // the previous pcut of this ion: fewer than 2000 scattering steps per particle (MCS_SLIM_DRAIN=0/1 forces it).
         const int slim_env = env_int("MCS_SLIM_DRAIN", -1);
         const bool slim = slim_env >= 0 ? slim_env != 0 : (h->last_steps_per_particle > 0 && h->last_steps_per_particle < 2000.0);
+        const bool custom = h->cfg.use_custom_epsB != 0 && !obl;  // custom eps_B build of the fast loop (parallel shocks; else general pass)
         void (*kern)(const DevParams) =
             debug ? (electron ? transport_kernel<true, true, false, false> : transport_kernel<true, false, false, false>)
+            : custom ? (electron ? transport_kernel<false, true, false, false, true> : transport_kernel<false, false, false, false, true>)
             : slim ? (electron ? (obl ? transport_kernel<false, true, true, true> : transport_kernel<false, true, false, true>)
                                : (obl ? transport_kernel<false, false, true, true> : transport_kernel<false, false, false, true>))
                    : (electron ? (obl ? transport_kernel<false, true, true, false> : transport_kernel<false, true, false, false>)

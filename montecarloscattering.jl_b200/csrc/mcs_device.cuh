@@ -1440,7 +1440,7 @@ __device__ __forceinline__ double mod2pi_bf(double v, bool& ok) {
 #else
 #define MCS_KERNEL_BOUNDS __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS)
 #endif
-template <bool DEBUG, bool ELECTRON, bool OBLIQUE, bool SLIM>
+template <bool DEBUG, bool ELECTRON, bool OBLIQUE, bool SLIM, bool CUSTOM = false>
 __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char mcs_smem[];
     const int ng = P.n_grid;
@@ -1465,7 +1465,10 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
 
     const uint32_t flags = P.flags;
     // the fast loop covers scattering configurations without per-pass field updates, detectors or debug streams
-    const bool fast_ok = !DEBUG && !(flags & (F_CUSTOM_EPSB | F_DONT_SCATTER | F_NO_FAST_LOOP)) && P.n_xspec == 0;
+    // custom eps_B (field beyond the end of the grid falls off as sqrt(x_grid_stop / x): per-pass gyro-period) is a compile-time
+    // variant of the fast loop: as a launch-uniform branch it cost the plain kernel 6 % (temporaries kept live, larger loop)
+    const bool fast_ok = !DEBUG && !(flags & (F_DONT_SCATTER | F_NO_FAST_LOOP)) && P.n_xspec == 0 && (CUSTOM || !(flags & F_CUSTOM_EPSB));
+    constexpr bool custom_cfg = CUSTOM;
     const bool rad_fast = ELECTRON && (flags & F_RAD_LOSSES);  // the fast loop applies radiation_loss itself, pass by pass
     const bool reflect_cfg = (flags & F_DONT_DSA) || P.inj_frac < 1;
 
@@ -1565,15 +1568,23 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         // do not change (pb and pperp shrink by the same factor).  Held in temporaries until the pass commits.
                         double p_use = 0.0, gam_use = 0.0, grt_u = grt, vgm_u = vgm, gper_u = gper;
                         bool lost_all = false;
-                        if (ELECTRON && rad_fast) {
-                            const double bmag = P.bt[iz], Bcmb = P.B_CMBz * zt.b[iz].x;
-                            p_use = radiation_loss(P, bmag * bmag + Bcmb * Bcmb, L.ptot, t_step);
-                            lost_all = !(p_use > 0.0);                               // fate 4: the general pass ends it
-                            gam_use = hypot(p_use / P.mc, 1.0);
-                            const double gd_z = zt.gd[iz];
-                            grt_u = p_use * P.c * gd_z;
-                            vgm_u = p_use * (1 / (gam_use * P.m));
-                            gper_u = p_use < P.pe_crit ? TWO_PI * P.gam_e_crit * P.mc * gd_z : TWO_PI * gam_use * P.mc * gd_z;
+                        if ((ELECTRON && rad_fast) || custom_cfg) {
+                            // the field of this pass as the general pass takes it (particle_loop.jl:239-247): the zone's, or with
+                            // custom eps_B beyond the end of the grid the last zone's falling off as sqrt(x_grid_stop / x)
+                            const bool off_grid = custom_cfg && x > P.x_grid_stop;
+                            const double bmag = off_grid ? P.bt[ng] * sqrt(P.x_grid_stop / x) : P.bt[iz];
+                            const double gd_z = off_grid ? 1 / (P.zz * bmag) : zt.gd[iz];
+                            if (ELECTRON && rad_fast) {
+                                const double Bcmb = P.B_CMBz * zt.b[iz].x;
+                                p_use = radiation_loss(P, bmag * bmag + Bcmb * Bcmb, L.ptot, t_step);
+                                lost_all = !(p_use > 0.0);                           // fate 4: the general pass ends it
+                                gam_use = hypot(p_use / P.mc, 1.0);
+                                grt_u = p_use * P.c * gd_z;
+                                vgm_u = p_use * (1 / (gam_use * P.m));
+                            } else {
+                                p_use = L.ptot; gam_use = L.gam_pf;
+                            }
+                            gper_u = (ELECTRON && p_use < P.pe_crit) ? TWO_PI * P.gam_e_crit * P.mc * gd_z : TWO_PI * gam_use * P.mc * gd_z;
                         } else if (ELECTRON) {
                             p_use = L.ptot; gam_use = L.gam_pf;
                         }
@@ -1665,7 +1676,8 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                                 if (x < P.x_grid_stop) {
                                     // prob_return.jl:59-84: just crossed the end of the grid -> place the PRP
                                     const double p_g = ELECTRON ? p_use : L.ptot, gam_g = ELECTRON ? gam_use : L.gam_pf;
-                                    const double g2 = p_g * P.c * 1.0 / (P.qcgs * P.bmag2);
+                                    const double gyro_tmp = (custom_cfg && x_n > P.x_grid_stop) ? sqrt(P.x_grid_stop / x_n) : 1.0;
+                                    const double g2 = p_g * P.c * gyro_tmp / (P.qcgs * P.bmag2);
                                     prp_n = x_n + 3 * (P.eta_mfp / 3 * g2 * p_g / (P.aa * P.mp * gam_g * P.u2));
                                 } else {
                                     pk |= (x < prp_n && x_n >= prp_n) | ELECTRON;  // PRP crossing: probability-of-return test

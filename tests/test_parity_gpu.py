@@ -346,17 +346,22 @@ def test_all_visible_gpus_nccl_match_one_gpu(clib):
     _multi_gpu_case(clib, n)
 
 
-@pytest.mark.parametrize("case", ["protons", "electrons_with_losses"])
+@pytest.mark.parametrize("case", ["protons", "electrons_with_losses", "custom_epsB"])
 def test_fast_loop_matches_general_path(clib, monkeypatch, case):
     """The two-speed kernel (fast loop + lane parking) against the same kernel with every pass on the general path
     (MCS_NO_FAST_LOOP=1): per particle the sequence of operations is the same, so integers are identical and the
     continuous state agrees to rounding (the two code paths may contract FMAs differently).  Electrons of config 5:
-    radiation_loss applied pass by pass inside the fast loop (momentum, Lorentz factor, gyro-radius and speed per pass)."""
+    radiation_loss applied pass by pass inside the fast loop (momentum, Lorentz factor, gyro-radius and speed per pass).
+    Custom eps_B: the gyro-period of a pass beyond the end of the grid follows the field's sqrt(x_grid_stop / x) fall-off."""
     if case == "protons":
         inp, i_ion = problem.planar_test_particle_input(20_000, momentum_cutoffs=LADDER[:5]), 1
-    else:
+    elif case == "electrons_with_losses":
         inp, i_ion = problem.multi_species_input(3000, momentum_cutoffs=problem.DEFAULT_PCUTS[:4]), 3
+    else:  # the bundled input with scattering switched on: eps_B profile, field falling off beyond the end of the grid
+        inp, i_ion = problem.ShockInput(no_scatter=False, no_dsa=False, n_pts_inj=4000, n_pts_pcut=5000, n_pts_pcut_hi=5000,
+                                        momentum_cutoffs=problem.DEFAULT_PCUTS[:8]), 1
     run = problem.setup_run(inp)
+    assert bool(inp.use_custom_epsB) == (case == "custom_epsB")
     sp = run.species[i_ion - 1]
     res = []
     for no_fast in ("0", "1"):
