@@ -556,10 +556,20 @@ static int launch_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_pr
         // the previous pcut of this ion: fewer than 2000 scattering steps per particle (MCS_SLIM_DRAIN=0/1 forces it).
         const int slim_env = env_int("MCS_SLIM_DRAIN", -1);
         const bool slim = slim_env >= 0 ? slim_env != 0 : (h->last_steps_per_particle > 0 && h->last_steps_per_particle < 2000.0);
+        // which optional per-pass features this launch needs; the two commonest masks have their own builds of the kernel
+        const int feat = (P.age_max > 0 ? FEAT_AGE : 0) | ((P.flags & F_TCUTS) ? FEAT_TCUTS : 0) | (P.feb_dn > 0 ? FEAT_FEB_DN : 0) |
+                         (((P.flags & F_DONT_DSA) || P.inj_frac < 1) ? FEAT_REFLECT : 0) | (P.energy_transfer_frac > 0 ? FEAT_ETF : 0);
+        const bool spec = env_int("MCS_PLAIN", 1) != 0 && !obl && (feat == 0 || feat == FEAT_ETF);
         const bool custom = h->cfg.use_custom_epsB != 0 && !obl;  // custom eps_B build of the fast loop (parallel shocks; else general pass)
         void (*kern)(const DevParams) =
             debug ? (electron ? transport_kernel<true, true, false, false> : transport_kernel<true, false, false, false>)
             : custom ? (electron ? transport_kernel<false, true, false, false, true> : transport_kernel<false, false, false, false, true>)
+            : (spec && feat == 0)
+                ? (slim ? (electron ? transport_kernel<false, true, false, true, false, 0> : transport_kernel<false, false, false, true, false, 0>)
+                        : (electron ? transport_kernel<false, true, false, false, false, 0> : transport_kernel<false, false, false, false, false, 0>))
+            : spec
+                ? (slim ? (electron ? transport_kernel<false, true, false, true, false, FEAT_ETF> : transport_kernel<false, false, false, true, false, FEAT_ETF>)
+                        : (electron ? transport_kernel<false, true, false, false, false, FEAT_ETF> : transport_kernel<false, false, false, false, false, FEAT_ETF>))
             : slim ? (electron ? (obl ? transport_kernel<false, true, true, true> : transport_kernel<false, true, false, true>)
                                : (obl ? transport_kernel<false, false, true, true> : transport_kernel<false, false, false, true>))
                    : (electron ? (obl ? transport_kernel<false, true, true, false> : transport_kernel<false, true, false, false>)

@@ -1390,6 +1390,9 @@ __device__ __noinline__ bool general_section(const DevParams& P, Lane& Lref, con
     return all_done;
 }
 
+// optional per-pass features, as a compile-time mask of transport_kernel (FEAT)
+enum : int { FEAT_AGE = 1, FEAT_TCUTS = 2, FEAT_FEB_DN = 4, FEAT_REFLECT = 8, FEAT_ETF = 16 };
+
 // lane status bits of the fast loop
 enum : uint32_t {
     ST_DOWN = 1u, ST_INJ = 2u, ST_XOLDLE0 = 4u, ST_PARKED = 8u, ST_NEEDPSP = 16u, ST_XSEL = 32u, ST_GTPMAX = 64u, ST_GTPCUT = 128u,
@@ -1440,7 +1443,7 @@ __device__ __forceinline__ double mod2pi_bf(double v, bool& ok) {
 #else
 #define MCS_KERNEL_BOUNDS __launch_bounds__(MCS_BLOCK, MCS_MIN_BLOCKS)
 #endif
-template <bool DEBUG, bool ELECTRON, bool OBLIQUE, bool SLIM, bool CUSTOM = false>
+template <bool DEBUG, bool ELECTRON, bool OBLIQUE, bool SLIM, bool CUSTOM = false, int FEAT = -1>
 __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char mcs_smem[];
     const int ng = P.n_grid;
@@ -1471,7 +1474,14 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
     constexpr bool custom_cfg = CUSTOM;
     const bool rad_fast = ELECTRON && (flags & F_RAD_LOSSES);  // the fast loop applies radiation_loss itself, pass by pass
     const double inv_mc = 1 / P.mc;
-    const bool reflect_cfg = (flags & F_DONT_DSA) || P.inj_frac < 1;
+    // FEAT >= 0: the host tells at compile time which optional features of a pass are switched on (FEAT_* bits: age limit,
+    // tcut tracking, downstream FEB, reflection for no-DSA / partial injection, energy transfer) and the loop does not test
+    // for the others.  As launch-uniform branches those five tests cost the plain configs 7-9 % (profiles/r02_variants.md).
+    // FEAT < 0: the generic build, every feature decided at run time.
+    constexpr bool known = FEAT >= 0;
+    const bool reflect_cfg = known ? (FEAT & FEAT_REFLECT) != 0 : ((flags & F_DONT_DSA) || P.inj_frac < 1);
+    const bool age_on = known ? (FEAT & FEAT_AGE) != 0 : P.age_max > 0, tcuts_on = known ? (FEAT & FEAT_TCUTS) != 0 : (flags & F_TCUTS) != 0,
+               feb_dn_on = known ? (FEAT & FEAT_FEB_DN) != 0 : P.feb_dn > 0, etf_on = known ? (FEAT & FEAT_ETF) != 0 : P.energy_transfer_frac > 0;
 
     Lane L;
     L.ptot = 1; L.pb = 0; L.pperp = 0; L.x = 0; L.prp_x = 0; L.acct = 0; L.phi = 0;
@@ -1523,7 +1533,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
         st = (L.down ? ST_DOWN : 0u) | (L.inj ? ST_INJ : 0u) | (L.x_old_le0 ? ST_XOLDLE0 : 0u) | (L.xsel ? ST_XSEL : 0u) |  \
              (L.ptot > P.pmax_cutoff ? ST_GTPMAX : 0u) | (L.ptot > P.pcut ? ST_GTPCUT : 0u) | (L.queue_empty ? ST_QEMPTY : 0u) | \
              ((L.ip >= 0 && L.parked) ? ST_PARKED : 0u) | (L.cs_valid ? L.cs_flags : 0u);                                   \
-        if (P.energy_transfer_frac > 0 && !L.inj && L.x_old_le0 && L.i_grid_old != L.i_grid) st |= ST_ETF;                  \
+        if (etf_on && !L.inj && L.x_old_le0 && L.i_grid_old != L.i_grid) st |= ST_ETF;                                      \
     } while (0)
             MCS_LOAD_LANE();
             int qn = L.qn;
@@ -1542,7 +1552,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                     // what the general pass must see before this pass: helix cap, a momentum above a cut-off (saved when
                     // downstream), pending energy transfer, age
                     bool park = (helix >= P.helix_cap) || (st & (ST_GTPMAX | ST_ETF));
-                    if (P.age_max > 0) park = park || acct > P.age_max;
+                    if (age_on) park = park || acct > P.age_max;
                     // downstream and above this pcut: the particle is saved by its next pass (particle_loop.jl:361-380): general pass.
                     // (Saving and refilling inside this loop was tried — MCS_TAIL, profiles/r02_variants.md — and lost 8 %:
                     // the extra vote per iteration and the larger loop cost more than the idle lanes it removed.)
@@ -1637,7 +1647,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         double acct_n = acct;
                         if (st & ST_DOWN) {
                             acct_n = acct + t_step * zb.x;
-                            if (flags & F_TCUTS) park = L.tcut <= P.n_tcuts && acct_n >= P.tcuts[L.tcut - 1];
+                            if (tcuts_on) park = L.tcut <= P.n_tcuts && acct_n >= P.tcuts[L.tcut - 1];
                         }
                         // Is this a plain pass?  Same zone, and inside the grid or between its end and the PRP.
                         const bool dn = x_n > x;
@@ -1647,7 +1657,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                         bool other = !(sn2 > 0.0) | park | (beyond & ((x < P.x_grid_stop) | !(x_n < prp_x) | ELECTRON));
                         if (ELECTRON) other |= lost_all;
                         if (st & ST_INJ) other |= x_n < P.feb_up;
-                        if (P.feb_dn > 0) other |= x_n > P.feb_dn;
+                        if (feb_dn_on) other |= x_n > P.feb_dn;
                         if (reflect_cfg) other |= (x_n <= 0) & (x > 0);
                         int ig_new = iz;
                         double prp_n = prp_x;
@@ -1666,7 +1676,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                             if (other) {
                             // anything the general pass would have to act on after the move -> nothing is committed
                             pk = park | !(sn2 > 0.0) | !(x_n == x_n) | (reflect_cfg && x_n <= 0 && x > 0 && !(st & ST_INJ)) |
-                                 (P.feb_dn > 0 && x_n > P.feb_dn) | (ELECTRON && lost_all);
+                                 (feb_dn_on && x_n > P.feb_dn) | (ELECTRON && lost_all);
                             // (not `other`: x_n < x_grid_stop <= prp_x, or x_grid_stop <= x, x_n < prp_x — neither test below fires)
                             if (x_n > 1.1 * prp_n) {
                                 // downstream_test (particle_loop.jl:609-633): far beyond the PRP -> escapes beyond 6.91 L_diff
@@ -1704,7 +1714,7 @@ __global__ void MCS_KERNEL_BOUNDS transport_kernel(const __grid_constant__ DevPa
                                 if (below_feb) st_n |= ST_PARKED;  // the next pass ends at the upstream FEB: general pass
                                 // energy transfer is due at the next pass of a not yet injected particle that changed zone
                                 // coming from x <= 0 (particle_loop.jl:235)
-                                if (P.energy_transfer_frac > 0 && !(st_n & ST_INJ) && x <= 0.0 && ig_new != iz) st_n |= ST_ETF;
+                                if (etf_on && !(st_n & ST_INJ) && x <= 0.0 && ig_new != iz) st_n |= ST_ETF;
                             }
                             go = !pk;
                         }

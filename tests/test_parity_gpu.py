@@ -413,12 +413,16 @@ def test_deterministic_tallies_run_to_run(clib):
 
 
 def test_both_builds_of_the_fast_loop_agree_bitwise(clib, monkeypatch):
-    """The library carries two builds of the fast loop (drain helpers inline / out of line) and picks one per launch from the
-    previous pcut's steps per particle (mcs_api.cu launch_pcut).  Same arithmetic, same lane schedule: every tally and every
+    """The library carries several builds of the fast loop — drain helpers inline / out of line, picked per launch from the
+    previous pcut's steps per particle; optional per-pass features compiled in or out by the config's feature mask, or all
+    tested at run time (mcs_api.cu launch_pcut).  Same arithmetic, same lane schedule: every tally and every
     saved record must be identical bit for bit whichever build runs — otherwise results would depend on the pick."""
     run = problem.setup_run(problem.relativistic_input(4000, momentum_cutoffs=problem.DEFAULT_PCUTS[:10]))
     out = []
-    for force in ("0", "1", None):
+    # third run: the host's own pick of the drain build, and the GENERIC kernel (every optional feature of a pass tested at
+    # run time, MCS_PLAIN=0) instead of the build compiled for this config's feature mask
+    for force, plain in (("0", "1"), ("1", "1"), (None, "0")):
+        monkeypatch.setenv("MCS_PLAIN", plain)
         if force is None:
             monkeypatch.delenv("MCS_SLIM_DRAIN", raising=False)
         else:
