@@ -9,4 +9,3 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tai
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --pcuts default > gpurun_out/final_bench_planar45.json 2>/dev/null; tail -1 gpurun_out/final_bench_planar45.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('planar 45-pcut ladder %.3e steps/s, %d pcuts run, %.0f ms' % (d['value'], d['config']['pcuts_run'], d['ms_per_step']))"
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --workload multi --all-species > gpurun_out/final_bench_multi_all.json 2>/dev/null; tail -1 gpurun_out/final_bench_multi_all.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('multi all species %.3e steps/s' % d['value'], {k:'%.3e' % v['steps_per_s'] for k,v in d['config']['species'].items()})"
 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --n-per-pcut 10000000 --generate-in-library > gpurun_out/final_bench_planar_1e7.json 2>/dev/null; tail -1 gpurun_out/final_bench_planar_1e7.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('planar 1e7 %.3e steps/s %.1f s/iter' % (d['value'], d['ms_per_step']/1e3))"
-python bench.py --steps 1 --warmup 1 --no-cpu-baseline --workload nonlinear --n-per-pcut 10000000 --generate-in-library > gpurun_out/final_bench_nonlinear_1e7.json 2>/dev/null; tail -1 gpurun_out/final_bench_nonlinear_1e7.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nonlinear 1e7 %.3e steps/s %.1f s/iter' % (d['value'], d['ms_per_step']/1e3))"
