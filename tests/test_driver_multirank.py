@@ -37,13 +37,14 @@ def _worker(rank, world, port, out):
     import oracle_engine
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     run = problem.setup_run(_inp())
-    e = make_engine(oracle_engine.load_oracle_library(), run)
+    e = make_engine(oracle_engine.load_oracle_library(), run, bin_thermal=True)
     comm = driver.TorchComm()
-    r = driver.main_loops(run, e, n_iters=1, comm=comm)[0][0]
+    r = driver.main_loops(run, e, n_iters=1, comm=comm, thermo=True)[0][0]
     if rank == 0:
         t = r["tallies"]
         pickle.dump(dict(pxx=r["pxx_flux"], en=r["energy_flux"], psd=t.psd, stats=t.stats, scalars=t.scalars,
-                         n_used=r["n_used"], n_saved=r["n_saved"], ncross=t.num_crossings, esc=t.esc_psd_feb_downstream),
+                         n_used=r["n_used"], n_saved=r["n_saved"], ncross=t.num_crossings, esc=t.esc_psd_feb_downstream,
+                         thpf=t.therm_d2N_pf, P_par=r["P_psd_par"], P_perp=r["P_psd_perp"], e_dens=r["energy_density_psd"]),
                     open(out, "wb"))
     dist.barrier()
     dist.destroy_process_group()
@@ -52,7 +53,7 @@ def _worker(rank, world, port, out):
 @pytest.mark.timeout(600)
 def test_two_ranks_match_one_rank(olib):
     run = problem.setup_run(_inp())
-    one = driver.main_loops(run, make_engine(olib, run), n_iters=1)[0][0]
+    one = driver.main_loops(run, make_engine(olib, run, bin_thermal=True), n_iters=1, thermo=True)[0][0]
     host = driver.main_loops(run, make_engine(olib, run), n_iters=1, host_pcut_loop=True)[0][0]
     assert np.array_equal(one["n_saved"], host["n_saved"]) and np.array_equal(one["pxx_flux"], host["pxx_flux"])
     with socket.socket() as s:
@@ -75,3 +76,8 @@ def test_two_ranks_match_one_rank(olib):
     assert rel_close(t.esc_psd_feb_downstream, two["esc"], 0) < 1e-11
     for k, v in t.scalars.items():
         assert two["scalars"][k] == pytest.approx(v, rel=1e-11)
+    # SURVEY 8(f1) across ranks: the thermal histograms are summed on the host like the other tallies, and the pressure consumer
+    # is fed the summed arrays (each rank's resident tallies are only its own share): same pressures as on one rank
+    assert rel_close(t.therm_d2N_pf, two["thpf"], 0) < 1e-11
+    for a, b in ((one["P_psd_par"], two["P_par"]), (one["P_psd_perp"], two["P_perp"]), (one["energy_density_psd"], two["e_dens"])):
+        assert np.all(np.isfinite(b)) and rel_close(a, b, 0) < 1e-10

@@ -246,3 +246,21 @@ def test_device_thermo_state_errors(clib):
     start_ion(e2, run)
     with pytest.raises(abi.McsError, match="bin_thermal"):
         e2.thermo(cosc, ptc, zp, 1e6)
+
+
+def test_thermo_with_the_reference_bin_centres_as_written(olib):
+    """`thermo_inputs(as_written=True)`: theta bounds sorted (initializers.jl:283) and pt_center = exp10(log10(p / m_p c)) taken
+    as g cm/s (thermo_calcs.jl:77-82) — momenta 1/(m_p c) = 2e13 too large, so a bin centre lands ~130 bins above its own bin.
+    The library does what it is given: finite output, equal to the restatement."""
+    run, prof = _case("planar")
+    sp = run.species[0]
+    e, t = _ion_tallies(olib, run, prof=prof)
+    cosc, ptc, zp = problem.thermo_inputs(run, prof, 0, as_written=True)
+    assert ptc[1] > 1e10 * run.psd_mom_min and np.all(np.diff(problem.psd_bounds(run, as_written=True)[1]) >= 0)
+    got = np.array(e.thermo(cosc, ptc, zp, sp.T))
+    want = thermo_restated(run, prof, sp, cosc, ptc, zp, sp.T, t.psd, t.therm_d2N_pf, t.num_crossings)
+    assert np.all(np.isfinite(got))
+    for k in range(4):
+        assert rel_close(got[k], want[k], 0) < 1e-12
+    for k in (1, 3, 10):
+        assert _bin_mom(run, float(ptc[k])) > k + 100
