@@ -919,6 +919,8 @@ int mcs_begin_ion(McsHandle* h, int32_t i_iter, int32_t i_ion, const McsSpecies*
     if (!h->have_profile) return fail(MCS_ERR_STATE, "mcs_set_profile first");
     if (n < 0 || n > h->cfg.n_pts_max) return fail(MCS_ERR_ARG, "n_pts exceeds n_pts_max");
     if (i_ion < 1 || i_ion > h->cfg.n_ions) return fail(MCS_ERR_ARG, "i_ion out of range");
+    /* the widths of the Philox counter fields (same checks, same messages as the CUDA library) */
+    if (first_global < 0 || first_global + n > 0x100000000ll) return fail(MCS_ERR_ARG, "global particle index exceeds 2^32 (RNG counter width)");
     if (n > 0 && (!pop->weight || !pop->ptot_pf || !pop->pb_pf || !pop->x_cm || !pop->grid || !pop->phi_rad))
         return fail(MCS_ERR_ARG, "weight/ptot_pf/pb_pf/x_cm/grid/phi_rad are required");
     h->sp = *sp; h->i_iter = i_iter; h->i_ion = i_ion; h->i_pcut = 0;
@@ -992,6 +994,7 @@ int mcs_begin_ion_generate(McsHandle* h, int32_t i_iter, int32_t i_ion, const Mc
 
 int mcs_run_pcut(McsHandle* h, int32_t i_pcut, double pcut, double pcut_prev, int64_t* n_saved, int64_t* n_steps) {
     if (!h || !h->have_ion) return fail(MCS_ERR_STATE, "mcs_begin_ion first");
+    if (i_pcut < 0 || i_pcut > 0xFFFF) return fail(MCS_ERR_ARG, "i_pcut outside the RNG counter's 16-bit field");
     h->i_pcut = i_pcut; h->pcut = pcut; h->pcut_prev = pcut_prev;
     int64_t n = h->n_use;
     /* main_loops.jl:184-197 */

@@ -83,6 +83,15 @@ def _size_cap_and_call_order(lib):
     e.run_pcut(1, run.pcuts[0], 0.0)
     with pytest.raises(abi.McsError):
         e.split_explicit(0, 0)                        # i_mult < 1
+    # widths of the Philox counter fields: errors at the boundary instead of a silent wrap that would reuse streams
+    e6 = make_engine(lib, run)
+    with pytest.raises(abi.McsError, match="2\\^32"):
+        start_ion(e6, run, pop=pop, first_global=2**32 - n + 1)   # last particle would get global index 2^32
+    start_ion(e6, run, pop=pop, first_global=2**32 - n)           # the last index that fits: accepted
+    with pytest.raises(abi.McsError, match="16-bit"):
+        e6.run_pcut(0x10000, run.pcuts[0], 0.0)
+    ns, _ = e6.run_pcut(0xFFFF, run.pcuts[0], 0.0)                # the largest pcut number that fits
+    assert ns >= 0
 
 
 def _nobody_survives(lib):
